@@ -1,0 +1,494 @@
+// mwrt_api.cu -- the extern "C" surface of libmwrt.so (include/mwrt.h): model handles, stage entry
+// points, and the plan that chains the kernels for a batch of profiles (device or host buffers).
+//
+// Boundary it replaces: TbCloudRTE(z,p,t,rh,frq,ang) / init_absmdl / satellite / execute() as called at
+// /root/reference/python_src/proc/PyRTlib_processing.py:123-127 -- see INTEGRATION.md.
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "mwrt_common.cuh"
+
+namespace mwrt {
+
+static thread_local std::string g_err;
+
+int fail_cuda(cudaError_t e, const char* what) {
+  g_err = std::string("CUDA error ") + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ") in " + what;
+  return (int)e;
+}
+int fail_arg(int code, const char* what) {
+  g_err = what;
+  return code;
+}
+
+// launchers defined in mwrt_absorption.cu / mwrt_rte.cu
+int absorption_launch(const ModelDev& m, int P, int L, int F, const double* p, const double* tk,
+                      const double* e, int e_is_rh, double* e_out, double* rho_out,
+                      const double* denliq, const double* denice, const double* frq, double* awet,
+                      double* adry, double* aliq, double* aice, int* status, cudaStream_t st);
+int vapor_launch(long long n, const double* tk, const double* rh, double* e, double* rho, cudaStream_t st);
+int rte_launch(int P, int L, int F, int A, const double* tk, const double* awet, const double* adry,
+               const double* aliq, const double* aice, const double* ds, const double* frq,
+               int from_sat, double emis, double* tbtotal, double* tbatm, double* tmr,
+               double* tauwet, double* taudry, double* tauliq, double* tauice, double* tau_layer,
+               int tl_angle, int* status, cudaStream_t st);
+int slant_path_launch(int P, int L, int A, const double* z, const double* p, const double* tk,
+                      const double* e, const double* angles, int ray_tracing, double* ds, int* status,
+                      cudaStream_t st);
+int bandpass_launch(int P, int C, int S, int A, const double* in, const double* w, double* out,
+                    cudaStream_t st);
+int dfma_peak(double* flops, double* mhz);
+
+struct mwrt_builtin_model {
+  const char* name;
+  mwrt_model_desc desc;
+};
+#include "mwrt_builtin_models.inc"
+
+}  // namespace mwrt
+
+using namespace mwrt;
+
+struct mwrt_model {
+  ModelDev dev;
+  double* d_tables;
+};
+
+struct mwrt_plan {
+  ModelDev model;
+  int L, F, A, flags, chunk;
+  double emis;
+  int C, S;          // band-pass (C == 0: off)
+  double* d_frq;
+  double* d_angles;
+  double* d_bpw;     // (C,S) weights or null (uniform)
+  // workspace for `cap` profiles
+  int cap;
+  double *w_awet, *w_adry, *w_aliq, *w_aice, *w_ds, *w_e;
+  double* w_mono[7];  // monochromatic RTE outputs when band-pass is on
+  // host-path resources (lazily created)
+  bool host_ready;
+  cudaStream_t s_h2d, s_comp, s_d2h;
+  cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
+  int hcap;
+  double* h_in[2][6];
+  double* h_out[2][7];
+  double* h_tl[2];
+  int* h_status[2];
+};
+
+extern "C" {
+
+int mwrt_version(void) { return MWRT_VERSION; }
+const char* mwrt_last_error(void) { return g_err.c_str(); }
+int mwrt_set_device(int device) {
+  MWRT_CUDA_OK(cudaSetDevice(device));
+  return 0;
+}
+int mwrt_get_device(int* device) {
+  if (!device) return fail_arg(MWRT_E_ARG, "mwrt_get_device: null argument");
+  MWRT_CUDA_OK(cudaGetDevice(device));
+  return 0;
+}
+
+int mwrt_builtin_model_count(void) { return k_n_builtin_models; }
+const char* mwrt_builtin_model_name(int i) {
+  if (i < 0 || i >= k_n_builtin_models) return nullptr;
+  return k_builtin_models[i].name;
+}
+int mwrt_builtin_model_desc(const char* name, mwrt_model_desc* out) {
+  if (!name || !out) return fail_arg(MWRT_E_ARG, "mwrt_builtin_model_desc: null argument");
+  for (int i = 0; i < k_n_builtin_models; ++i)
+    if (strcmp(name, k_builtin_models[i].name) == 0) {
+      *out = k_builtin_models[i].desc;
+      return 0;
+    }
+  g_err = std::string("absorption model '") + name + "' is not implemented";
+  return MWRT_E_MODEL;
+}
+
+int mwrt_model_create_custom(const mwrt_model_desc* d, mwrt_model** out) {
+  if (!d || !out || !d->h2o_lines || !d->o2_lines)
+    return fail_arg(MWRT_E_ARG, "mwrt_model_create_custom: null argument");
+  if (d->n_h2o < 1 || d->n_h2o > MWRT_MAX_H2O_LINES || d->n_o2 < 1 || d->n_o2 > MWRT_MAX_O2_LINES)
+    return fail_arg(MWRT_E_ARG, "mwrt_model_create_custom: line count out of range");
+  if (d->o2_mixing != 1 && d->o2_mixing != 2)
+    return fail_arg(MWRT_E_ARG, "mwrt_model_create_custom: o2_mixing must be 1 or 2");
+  mwrt_model* m = new mwrt_model();
+  const int nh = d->n_h2o * MWRT_H2O_NCOL, no = d->n_o2 * MWRT_O2_NCOL;
+  std::vector<double> host((size_t)nh + no);
+  memcpy(host.data(), d->h2o_lines, sizeof(double) * nh);
+  memcpy(host.data() + nh, d->o2_lines, sizeof(double) * no);
+  cudaError_t e = cudaMalloc(&m->d_tables, sizeof(double) * host.size());
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->d_tables, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    delete m;
+    return fail_cuda(e, "mwrt_model_create_custom");
+  }
+  ModelDev& v = m->dev;
+  v.n_h2o = d->n_h2o; v.n_o2 = d->n_o2;
+  v.h2o_sd = d->h2o_sd; v.o2_mixing = d->o2_mixing; v.o2_dens118 = d->o2_dens118;
+  v.o2_sd118 = d->o2_sd118; v.n2_fdep = d->n2_fdep; v.liq_model = d->liq_model;
+  v.h2o_reftline = d->h2o_reftline; v.h2o_reftcon = d->h2o_reftcon; v.h2o_cf = d->h2o_cf;
+  v.h2o_xcf = d->h2o_xcf; v.h2o_cs = d->h2o_cs; v.h2o_xcs = d->h2o_xcs;
+  v.h2o_pvap_div = d->h2o_pvap_div; v.h2o_den_const = d->h2o_den_const;
+  v.h2o_line_const = d->h2o_line_const;
+  v.o2_x = d->o2_x; v.o2_wb300 = d->o2_wb300; v.o2_pvap_div = d->o2_pvap_div;
+  v.o2_h2o_broad = d->o2_h2o_broad; v.o2_nonres = d->o2_nonres;
+  v.o2_abs_const = d->o2_abs_num / d->o2_abs_den; v.o2_iso = d->o2_iso;
+  v.n2_l = d->n2_l; v.n2_m = d->n2_m; v.n2_n = d->n2_n;
+  v.tables = m->d_tables;
+  v.n_table = nh + no;
+  *out = m;
+  return 0;
+}
+
+int mwrt_model_create(const char* name, mwrt_model** out) {
+  mwrt_model_desc d;
+  int rc = mwrt_builtin_model_desc(name, &d);
+  if (rc) return rc;
+  return mwrt_model_create_custom(&d, out);
+}
+
+int mwrt_model_destroy(mwrt_model* m) {
+  if (!m) return 0;
+  cudaFree(m->d_tables);
+  delete m;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ stage API
+int mwrt_vapor_f64(int64_t n, const double* tk, const double* rh, double* e, double* rho, void* stream) {
+  if (n <= 0 || !tk || !rh || !e) return fail_arg(MWRT_E_ARG, "mwrt_vapor_f64: bad argument");
+  return vapor_launch(n, tk, rh, e, rho, (cudaStream_t)stream);
+}
+
+int mwrt_absorption_f64(const mwrt_model* m, int P, int L, int F, const double* p, const double* tk,
+                        const double* e, const double* denliq, const double* denice, const double* frq,
+                        double* awet, double* adry, double* aliq, double* aice, int32_t* status,
+                        void* stream) {
+  if (!m || P <= 0 || L <= 0 || F <= 0 || !p || !tk || !e || !frq || !awet || !adry)
+    return fail_arg(MWRT_E_ARG, "mwrt_absorption_f64: bad argument");
+  return absorption_launch(m->dev, P, L, F, p, tk, e, 0, nullptr, nullptr, denliq, denice, frq, awet,
+                           adry, aliq, aice, status, (cudaStream_t)stream);
+}
+
+int mwrt_slant_path_f64(int P, int L, int A, const double* z, const double* p, const double* tk,
+                        const double* e, const double* angles, int ray_tracing, double* ds,
+                        int32_t* status, void* stream) {
+  if (P <= 0 || L <= 0 || A <= 0 || !z || !angles || !ds)
+    return fail_arg(MWRT_E_ARG, "mwrt_slant_path_f64: bad argument");
+  if (ray_tracing && (!p || !tk || !e))
+    return fail_arg(MWRT_E_ARG, "mwrt_slant_path_f64: ray tracing needs p, tk, e");
+  return slant_path_launch(P, L, A, z, p, tk, e, angles, ray_tracing, ds, status, (cudaStream_t)stream);
+}
+
+int mwrt_rte_f64(int P, int L, int F, int A, const double* tk, const double* awet, const double* adry,
+                 const double* aliq, const double* aice, const double* ds, const double* frq,
+                 int from_sat, double emissivity, double* tbtotal, double* tbatm, double* tmr,
+                 double* tauwet, double* taudry, double* tauliq, double* tauice, double* tau_layer,
+                 int tau_layer_angle, int32_t* status, void* stream) {
+  if (P <= 0 || L <= 1 || F <= 0 || A <= 0 || !tk || !awet || !adry || !ds || !frq)
+    return fail_arg(MWRT_E_ARG, "mwrt_rte_f64: bad argument");
+  if ((aliq == nullptr) != (aice == nullptr))
+    return fail_arg(MWRT_E_ARG, "mwrt_rte_f64: aliq and aice must be given together");
+  if (tau_layer && (tau_layer_angle < 0 || tau_layer_angle >= A))
+    return fail_arg(MWRT_E_ARG, "mwrt_rte_f64: tau_layer_angle out of range");
+  return rte_launch(P, L, F, A, tk, awet, adry, aliq, aice, ds, frq, from_sat, emissivity, tbtotal,
+                    tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tau_layer_angle, status,
+                    (cudaStream_t)stream);
+}
+
+int mwrt_bandpass_f64(int P, int C, int S, int A, const double* in, const double* w, double* out,
+                      void* stream) {
+  if (P <= 0 || C <= 0 || S <= 0 || A <= 0 || !in || !out)
+    return fail_arg(MWRT_E_ARG, "mwrt_bandpass_f64: bad argument");
+  return bandpass_launch(P, C, S, A, in, w, out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------ plan
+static void plan_free_ws(mwrt_plan* pl) {
+  cudaFree(pl->w_awet); cudaFree(pl->w_adry); cudaFree(pl->w_aliq); cudaFree(pl->w_aice);
+  cudaFree(pl->w_ds); cudaFree(pl->w_e);
+  for (int i = 0; i < 7; ++i) cudaFree(pl->w_mono[i]);
+  pl->w_awet = pl->w_adry = pl->w_aliq = pl->w_aice = pl->w_ds = pl->w_e = nullptr;
+  for (int i = 0; i < 7; ++i) pl->w_mono[i] = nullptr;
+  pl->cap = 0;
+}
+
+static int plan_reserve(mwrt_plan* pl, int cap) {
+  if (cap <= pl->cap) return 0;
+  plan_free_ws(pl);
+  const size_t pfl = sizeof(double) * (size_t)cap * pl->F * pl->L;
+  MWRT_CUDA_OK(cudaMalloc(&pl->w_awet, pfl));
+  MWRT_CUDA_OK(cudaMalloc(&pl->w_adry, pfl));
+  if (pl->flags & MWRT_F_CLOUDY) {
+    MWRT_CUDA_OK(cudaMalloc(&pl->w_aliq, pfl));
+    MWRT_CUDA_OK(cudaMalloc(&pl->w_aice, pfl));
+  }
+  MWRT_CUDA_OK(cudaMalloc(&pl->w_ds, sizeof(double) * (size_t)cap * pl->A * pl->L));
+  MWRT_CUDA_OK(cudaMalloc(&pl->w_e, sizeof(double) * (size_t)cap * pl->L));
+  if (pl->C > 0)
+    for (int i = 0; i < 7; ++i)
+      MWRT_CUDA_OK(cudaMalloc(&pl->w_mono[i], sizeof(double) * (size_t)cap * pl->F * pl->A));
+  pl->cap = cap;
+  return 0;
+}
+
+static int default_chunk(int L, int F, int flags) {
+  // bound the (chunk,F,L) absorption workspace to ~1 GiB; it is streamed once (write, then read) and
+  // costs < 5 % of the FP64 time even when it spills out of the 126 MB L2
+  const double per_profile = 8.0 * F * L * ((flags & MWRT_F_CLOUDY) ? 4 : 2);
+  double c = (1024.0 * 1024.0 * 1024.0) / per_profile;
+  if (c < 64) c = 64;
+  if (c > (1 << 20)) c = (1 << 20);
+  return (int)c;
+}
+
+int mwrt_plan_create(const mwrt_model* m, int L, int F, int A, const double* frq, const double* angles,
+                     int flags, int chunk_profiles, mwrt_plan** out) {
+  if (!m || !frq || !angles || !out || L < 2 || F < 1 || A < 1)
+    return fail_arg(MWRT_E_ARG, "mwrt_plan_create: bad argument");
+  mwrt_plan* pl = new mwrt_plan();
+  memset(pl, 0, sizeof(*pl));
+  pl->model = m->dev;
+  pl->L = L; pl->F = F; pl->A = A; pl->flags = flags;
+  pl->chunk = chunk_profiles > 0 ? chunk_profiles : default_chunk(L, F, flags);
+  pl->emis = 1.0;
+  cudaError_t e = cudaMalloc(&pl->d_frq, sizeof(double) * F);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_angles, sizeof(double) * A);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_frq, frq, sizeof(double) * F, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_angles, angles, sizeof(double) * A, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(pl->d_frq); cudaFree(pl->d_angles);
+    delete pl;
+    return fail_cuda(e, "mwrt_plan_create");
+  }
+  *out = pl;
+  return 0;
+}
+
+static void plan_free_host(mwrt_plan* pl) {
+  if (!pl->host_ready) return;
+  for (int s = 0; s < 2; ++s) {
+    for (int i = 0; i < 6; ++i) cudaFree(pl->h_in[s][i]);
+    for (int i = 0; i < 7; ++i) cudaFree(pl->h_out[s][i]);
+    cudaFree(pl->h_tl[s]);
+    cudaFree(pl->h_status[s]);
+    cudaEventDestroy(pl->ev_h2d[s]); cudaEventDestroy(pl->ev_comp[s]); cudaEventDestroy(pl->ev_d2h[s]);
+  }
+  cudaStreamDestroy(pl->s_h2d); cudaStreamDestroy(pl->s_comp); cudaStreamDestroy(pl->s_d2h);
+  pl->host_ready = false;
+  pl->hcap = 0;
+}
+
+int mwrt_plan_destroy(mwrt_plan* pl) {
+  if (!pl) return 0;
+  plan_free_host(pl);
+  plan_free_ws(pl);
+  cudaFree(pl->d_frq); cudaFree(pl->d_angles); cudaFree(pl->d_bpw);
+  delete pl;
+  return 0;
+}
+
+int mwrt_plan_set_emissivity(mwrt_plan* pl, double es) {
+  if (!pl) return fail_arg(MWRT_E_ARG, "mwrt_plan_set_emissivity: null plan");
+  pl->emis = es;
+  return 0;
+}
+
+int mwrt_plan_set_bandpass(mwrt_plan* pl, int C, int S, const double* weights) {
+  if (!pl) return fail_arg(MWRT_E_ARG, "mwrt_plan_set_bandpass: null plan");
+  if (C <= 0 || S <= 0 || (long long)C * S != pl->F)
+    return fail_arg(MWRT_E_ARG, "mwrt_plan_set_bandpass: C*S must equal F");
+  plan_free_ws(pl);
+  plan_free_host(pl);
+  cudaFree(pl->d_bpw);
+  pl->d_bpw = nullptr;
+  if (weights) {
+    MWRT_CUDA_OK(cudaMalloc(&pl->d_bpw, sizeof(double) * C * S));
+    MWRT_CUDA_OK(cudaMemcpy(pl->d_bpw, weights, sizeof(double) * C * S, cudaMemcpyHostToDevice));
+  }
+  pl->C = C; pl->S = S;
+  return 0;
+}
+
+int mwrt_plan_launch_count(const mwrt_plan* pl, int P) {
+  if (!pl || P <= 0) return 0;
+  const int nchunk = (P + pl->chunk - 1) / pl->chunk;
+  return nchunk * (3 + (pl->C > 0 ? 7 : 0));
+}
+
+// one chunk: device pointers already offset to the chunk's first profile
+static int forward_chunk(mwrt_plan* pl, int P, const mwrt_profiles& in, const mwrt_outputs& out,
+                         cudaStream_t st) {
+  const bool cloudy = pl->flags & MWRT_F_CLOUDY;
+  const bool rt = pl->flags & MWRT_F_RAY_TRACING;
+  const int L = pl->L, F = pl->F, A = pl->A;
+  if (out.status) MWRT_CUDA_OK(cudaMemsetAsync(out.status, 0, sizeof(int) * (size_t)P, st));
+  // kernel 1: vapour pressure + absorption (e is kept for the refractivity of kernel 2)
+  int rc = absorption_launch(pl->model, P, L, F, in.p, in.tk, in.rh, /*e_is_rh=*/1, pl->w_e, nullptr,
+                             cloudy ? in.denliq : nullptr, cloudy ? in.denice : nullptr, pl->d_frq,
+                             pl->w_awet, pl->w_adry, cloudy ? pl->w_aliq : nullptr,
+                             cloudy ? pl->w_aice : nullptr, out.status, st);
+  if (rc) return rc;
+  // kernel 2: slant path
+  rc = slant_path_launch(P, L, A, in.z, in.p, in.tk, pl->w_e, pl->d_angles, rt ? 1 : 0, pl->w_ds,
+                         out.status, st);
+  if (rc) return rc;
+  // kernel 3: RTE (+ band-pass epilogue)
+  double* tl = (pl->flags & MWRT_F_TAU_LAYERS) ? out.tau_layer : nullptr;
+  double* dst[7] = {out.tbtotal, out.tbatm, out.tmr, out.tauwet, out.taudry, out.tauliq, out.tauice};
+  double* mono[7];
+  for (int i = 0; i < 7; ++i) mono[i] = (pl->C > 0) ? (dst[i] ? pl->w_mono[i] : nullptr) : dst[i];
+  rc = rte_launch(P, L, F, A, in.tk, pl->w_awet, pl->w_adry, cloudy ? pl->w_aliq : nullptr,
+                  cloudy ? pl->w_aice : nullptr, pl->w_ds, pl->d_frq,
+                  (pl->flags & MWRT_F_FROM_SAT) ? 1 : 0, pl->emis, mono[0], mono[1], mono[2], mono[3],
+                  mono[4], mono[5], mono[6], tl, 0, out.status, st);
+  if (rc) return rc;
+  if (pl->C > 0)
+    for (int i = 0; i < 7; ++i)
+      if (dst[i]) {
+        rc = bandpass_launch(P, pl->C, pl->S, A, mono[i], pl->d_bpw, dst[i], st);
+        if (rc) return rc;
+      }
+  return 0;
+}
+
+static int check_io(const mwrt_plan* pl, int P, const mwrt_profiles* in, const mwrt_outputs* out,
+                    const char* who) {
+  if (!pl || !in || !out || P <= 0) return fail_arg(MWRT_E_ARG, who);
+  if (!in->z || !in->p || !in->tk || !in->rh) return fail_arg(MWRT_E_ARG, "forward: z/p/tk/rh required");
+  if ((pl->flags & MWRT_F_CLOUDY) && (!in->denliq || !in->denice))
+    return fail_arg(MWRT_E_ARG, "forward: MWRT_F_CLOUDY needs denliq and denice");
+  if (out->tau_layer && !(pl->flags & MWRT_F_TAU_LAYERS))
+    return fail_arg(MWRT_E_ARG, "forward: tau_layer needs MWRT_F_TAU_LAYERS");
+  return 0;
+}
+
+static mwrt_profiles offset_in(const mwrt_profiles& in, size_t off) {
+  mwrt_profiles r = in;
+  r.z += off; r.p += off; r.tk += off; r.rh += off;
+  if (r.denliq) r.denliq += off;
+  if (r.denice) r.denice += off;
+  return r;
+}
+static mwrt_outputs offset_out(const mwrt_outputs& o, size_t off_pfa, size_t off_pfl, size_t off_p) {
+  mwrt_outputs r = o;
+  double** f[7] = {&r.tbtotal, &r.tbatm, &r.tmr, &r.tauwet, &r.taudry, &r.tauliq, &r.tauice};
+  for (int i = 0; i < 7; ++i)
+    if (*f[i]) *f[i] += off_pfa;
+  if (r.tau_layer) r.tau_layer += off_pfl;
+  if (r.status) r.status += off_p;
+  return r;
+}
+
+int mwrt_plan_forward_device(mwrt_plan* pl, int P, const mwrt_profiles* in, const mwrt_outputs* out,
+                             void* stream) {
+  int rc = check_io(pl, P, in, out, "mwrt_plan_forward_device: bad argument");
+  if (rc) return rc;
+  const int chunk = std::min(P, pl->chunk);
+  rc = plan_reserve(pl, chunk);
+  if (rc) return rc;
+  const int Fo = pl->C > 0 ? pl->C : pl->F;
+  for (int p0 = 0; p0 < P; p0 += chunk) {
+    const int n = std::min(chunk, P - p0);
+    rc = forward_chunk(pl, n, offset_in(*in, (size_t)p0 * pl->L),
+                       offset_out(*out, (size_t)p0 * Fo * pl->A, (size_t)p0 * pl->F * pl->L, p0),
+                       (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static int plan_host_init(mwrt_plan* pl, int hcap) {
+  if (pl->host_ready && hcap <= pl->hcap) return 0;
+  plan_free_host(pl);
+  MWRT_CUDA_OK(cudaStreamCreateWithFlags(&pl->s_h2d, cudaStreamNonBlocking));
+  MWRT_CUDA_OK(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
+  MWRT_CUDA_OK(cudaStreamCreateWithFlags(&pl->s_d2h, cudaStreamNonBlocking));
+  const int Fo = pl->C > 0 ? pl->C : pl->F;
+  for (int s = 0; s < 2; ++s) {
+    MWRT_CUDA_OK(cudaEventCreateWithFlags(&pl->ev_h2d[s], cudaEventDisableTiming));
+    MWRT_CUDA_OK(cudaEventCreateWithFlags(&pl->ev_comp[s], cudaEventDisableTiming));
+    MWRT_CUDA_OK(cudaEventCreateWithFlags(&pl->ev_d2h[s], cudaEventDisableTiming));
+    const int nin = (pl->flags & MWRT_F_CLOUDY) ? 6 : 4;
+    for (int i = 0; i < nin; ++i)
+      MWRT_CUDA_OK(cudaMalloc(&pl->h_in[s][i], sizeof(double) * (size_t)hcap * pl->L));
+    for (int i = 0; i < 7; ++i)
+      MWRT_CUDA_OK(cudaMalloc(&pl->h_out[s][i], sizeof(double) * (size_t)hcap * Fo * pl->A));
+    if (pl->flags & MWRT_F_TAU_LAYERS)
+      MWRT_CUDA_OK(cudaMalloc(&pl->h_tl[s], sizeof(double) * (size_t)hcap * pl->F * pl->L));
+    MWRT_CUDA_OK(cudaMalloc(&pl->h_status[s], sizeof(int) * (size_t)hcap));
+  }
+  pl->host_ready = true;
+  pl->hcap = hcap;
+  return 0;
+}
+
+int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const mwrt_outputs* out) {
+  int rc = check_io(pl, P, in, out, "mwrt_plan_forward_host: bad argument");
+  if (rc) return rc;
+  // >= 4 chunks when the batch is large enough, so copies hide behind kernels
+  int chunk = std::min(pl->chunk, std::max((P + 3) / 4, 2048));
+  chunk = std::min(chunk, P);
+  rc = plan_reserve(pl, chunk);
+  if (rc) return rc;
+  rc = plan_host_init(pl, chunk);
+  if (rc) return rc;
+  const int L = pl->L, F = pl->F, A = pl->A;
+  const int Fo = pl->C > 0 ? pl->C : F;
+  const bool cloudy = pl->flags & MWRT_F_CLOUDY;
+  const double* hin[6] = {in->z, in->p, in->tk, in->rh, in->denliq, in->denice};
+  double* hout[7] = {out->tbtotal, out->tbatm, out->tmr, out->tauwet, out->taudry, out->tauliq, out->tauice};
+  int c = 0;
+  for (int p0 = 0; p0 < P; p0 += chunk, ++c) {
+    const int n = std::min(chunk, P - p0);
+    const int s = c & 1;
+    // input slot s is free once the kernels of chunk c-2 have run
+    if (c >= 2) MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_h2d, pl->ev_comp[s], 0));
+    for (int i = 0; i < (cloudy ? 6 : 4); ++i)
+      MWRT_CUDA_OK(cudaMemcpyAsync(pl->h_in[s][i], hin[i] + (size_t)p0 * L, sizeof(double) * (size_t)n * L,
+                                   cudaMemcpyHostToDevice, pl->s_h2d));
+    MWRT_CUDA_OK(cudaEventRecord(pl->ev_h2d[s], pl->s_h2d));
+    MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_comp, pl->ev_h2d[s], 0));
+    // output slot s is free once chunk c-2 has been copied back
+    if (c >= 2) MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_comp, pl->ev_d2h[s], 0));
+    mwrt_profiles din = {pl->h_in[s][0], pl->h_in[s][1], pl->h_in[s][2], pl->h_in[s][3],
+                         cloudy ? pl->h_in[s][4] : nullptr, cloudy ? pl->h_in[s][5] : nullptr};
+    mwrt_outputs dout;
+    double** df[7] = {&dout.tbtotal, &dout.tbatm, &dout.tmr, &dout.tauwet, &dout.taudry, &dout.tauliq, &dout.tauice};
+    for (int i = 0; i < 7; ++i) *df[i] = hout[i] ? pl->h_out[s][i] : nullptr;
+    dout.tau_layer = out->tau_layer ? pl->h_tl[s] : nullptr;
+    dout.status = pl->h_status[s];
+    rc = forward_chunk(pl, n, din, dout, pl->s_comp);
+    if (rc) return rc;
+    MWRT_CUDA_OK(cudaEventRecord(pl->ev_comp[s], pl->s_comp));
+    MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_d2h, pl->ev_comp[s], 0));
+    for (int i = 0; i < 7; ++i)
+      if (hout[i])
+        MWRT_CUDA_OK(cudaMemcpyAsync(hout[i] + (size_t)p0 * Fo * A, pl->h_out[s][i],
+                                     sizeof(double) * (size_t)n * Fo * A, cudaMemcpyDeviceToHost, pl->s_d2h));
+    if (out->tau_layer)
+      MWRT_CUDA_OK(cudaMemcpyAsync(out->tau_layer + (size_t)p0 * F * L, pl->h_tl[s],
+                                   sizeof(double) * (size_t)n * F * L, cudaMemcpyDeviceToHost, pl->s_d2h));
+    if (out->status)
+      MWRT_CUDA_OK(cudaMemcpyAsync(out->status + p0, pl->h_status[s], sizeof(int) * (size_t)n,
+                                   cudaMemcpyDeviceToHost, pl->s_d2h));
+    MWRT_CUDA_OK(cudaEventRecord(pl->ev_d2h[s], pl->s_d2h));
+  }
+  MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_d2h));
+  MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_comp));
+  return 0;
+}
+
+int mwrt_measure_dfma_peak(double* flops_per_s, double* sm_clock_mhz_est) {
+  if (!flops_per_s) return fail_arg(MWRT_E_ARG, "mwrt_measure_dfma_peak: null argument");
+  return dfma_peak(flops_per_s, sm_clock_mhz_est);
+}
+
+}  // extern "C"

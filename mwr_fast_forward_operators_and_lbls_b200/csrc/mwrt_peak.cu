@@ -1,0 +1,76 @@
+// mwrt_peak.cu -- self-measured FP64 roofline denominator.
+//
+// MEASURED_PEAKS.json carries HBM and bf16 tensor peaks only; this path is bound by the FP64 pipe
+// (SURVEY.md 8(d)), so bench.py measures a DFMA-stream peak on the same GPU, in the same run, and
+// reports roofline fractions "of self-measured DFMA peak" (nominal: 148 SM x 64 DFMA/clk x 2 x 1.965 GHz
+// = 37.2 TFLOP/s).
+#include "mwrt_common.cuh"
+
+namespace mwrt {
+
+constexpr int kChains = 8;
+constexpr int kInner = 512;
+
+__global__ void __launch_bounds__(256) k_dfma(double* out, int outer, long long* clk) {
+  double x[kChains];
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) x[c] = 1.0 + 1e-9 * (threadIdx.x + c);
+  const double a = 1.0000000001, b = 1e-12;
+  long long t0 = clock64();
+  for (int o = 0; o < outer; ++o) {
+#pragma unroll 8
+    for (int i = 0; i < kInner; ++i) {
+#pragma unroll
+      for (int c = 0; c < kChains; ++c) x[c] = fma(x[c], a, b);
+    }
+  }
+  long long t1 = clock64();
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < kChains; ++c) s += x[c];
+  if (s == 123.456) out[0] = s;  // keep the chains alive
+  if (blockIdx.x == 0 && threadIdx.x == 0 && clk) clk[0] = t1 - t0;
+}
+
+int dfma_peak(double* flops, double* mhz) {
+  int dev = 0, nsm = 0;
+  MWRT_CUDA_OK(cudaGetDevice(&dev));
+  MWRT_CUDA_OK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  double* d_out = nullptr;
+  long long* d_clk = nullptr;
+  MWRT_CUDA_OK(cudaMalloc(&d_out, sizeof(double)));
+  MWRT_CUDA_OK(cudaMalloc(&d_clk, sizeof(long long)));
+  cudaEvent_t e0, e1;
+  MWRT_CUDA_OK(cudaEventCreate(&e0));
+  MWRT_CUDA_OK(cudaEventCreate(&e1));
+  const int blocks = nsm * 8, threads = 256, outer = 64;
+  k_dfma<<<blocks, threads>>>(d_out, 8, nullptr);  // warm-up
+  double best = 0.0, best_mhz = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    MWRT_CUDA_OK(cudaEventRecord(e0));
+    k_dfma<<<blocks, threads>>>(d_out, outer, d_clk);
+    MWRT_CUDA_OK(cudaEventRecord(e1));
+    MWRT_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    MWRT_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    long long clk = 0;
+    MWRT_CUDA_OK(cudaMemcpy(&clk, d_clk, sizeof(clk), cudaMemcpyDeviceToHost));
+    const double fl = 2.0 * (double)blocks * threads * (double)outer * kInner * kChains;
+    const double v = fl / (ms * 1e-3);
+    if (v > best) {
+      best = v;
+      // block 0's cycle count over the whole-kernel time underestimates the clock slightly
+      // (waves): blocks = 8/SM x 256 thr all resident, so one wave.
+      best_mhz = (double)clk / (ms * 1e-3) / 1e6;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  cudaFree(d_clk);
+  *flops = best;
+  if (mhz) *mhz = best_mhz;
+  return 0;
+}
+
+}  // namespace mwrt

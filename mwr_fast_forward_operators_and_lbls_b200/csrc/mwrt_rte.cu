@@ -1,0 +1,341 @@
+// mwrt_rte.cu -- kernels 2 and 3: slant path and the radiative-transfer integral.
+//
+// Kernel 2 (k_slant_path): RTEquation.refractivity + RTEquation.ray_tracing, or the plane-parallel
+//   diff(z)/sin(elev) the reference actually runs (the 6-argument constructor at
+//   /root/reference/python_src/proc/PyRTlib_processing.py:123 keeps ray_tracing=False).  SURVEY.md A.9.
+// Kernel 3 (k_rte): RTEquation.exponential_integration (layer optical depths), RTEquation.planck
+//   (downwelling recursion + cosmic background, or upwelling) and RTEquation.bright.  SURVEY.md A.8/A.10.
+//
+// Mapping: thread = (profile, frequency); it walks the layers once, in the oracle's order, and carries
+// NA viewing angles in registers -- the layer-mean absorption (2-4 log) and the Planck term (1 exp)
+// are computed once per layer and shared by all angles, and the NA exp(-tau) chains give the FP64 pipe
+// NA-way instruction-level parallelism.  One exp per (layer, angle): the transmission to the observer
+// is carried as a running product instead of PyRTlib's second exp(-tauprof).
+#include "mwrt_common.cuh"
+
+namespace mwrt {
+
+constexpr int kRteThreads = 128;
+
+// One layer of exponential_integration without the ds factor.  Negative input -> NaN
+// (PyRTlib raises ValueError; the caller flags the profile with MWRT_ST_NEG_ABS).
+__device__ __forceinline__ double layer_mean(double x0, double x1, bool zeroflg, bool& neg) {
+  if (x0 < 0.0 || x1 < 0.0) {
+    neg = true;
+    return nan("");
+  }
+  if (fabs(x1 - x0) < 1e-09) return x1;
+  if (x0 == 0.0 || x1 == 0.0) return zeroflg ? (x1 + x0) * 0.5 : 0.0;
+  return (x1 - x0) / log(x1 / x0);
+}
+
+__device__ __forceinline__ double planck_mod(double hvk, double t) { return 1.0 / (exp(hvk / t) - 1.0); }
+__device__ __forceinline__ double bright(double hvk, double b) {
+  if (b > 0.0 || isnan(b)) return hvk / log(1.0 + 1.0 / b);
+  return 0.0;
+}
+
+template <int NA, bool CLOUDY>
+__global__ void __launch_bounds__(kRteThreads)
+k_rte(const int P, const int L, const int F, const int A, const double* __restrict__ tk,
+      const double* __restrict__ awet, const double* __restrict__ adry,
+      const double* __restrict__ aliq, const double* __restrict__ aice,
+      const double* __restrict__ ds, const double* __restrict__ frq, const int from_sat,
+      const double emis, double* __restrict__ tbtotal, double* __restrict__ tbatm,
+      double* __restrict__ tmr, double* __restrict__ tauwet, double* __restrict__ taudry,
+      double* __restrict__ tauliq, double* __restrict__ tauice, double* __restrict__ tau_layer,
+      const int tl_angle, int* __restrict__ status) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)P * F) return;
+  const long long p = idx / F;
+  const int jf = (int)(idx - p * F);
+  const int a0 = blockIdx.y * NA;
+  const long long row = idx * (long long)L;  // (p*F + jf)*L
+  const double* tkp = tk + p * L;
+  const double* dsp = ds + (p * A + a0) * (long long)L;
+  const double hvk = (frq[jf] * 1e9) * kPlanckH / kBoltzmannK;
+
+  double tauprof[NA], batm[NA], trans[NA], sw[NA], sd[NA], sl[NA], si[NA];
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    tauprof[a] = 0.0; batm[a] = 0.0; trans[a] = 1.0;
+    sw[a] = 0.0; sd[a] = 0.0; sl[a] = 0.0; si[a] = 0.0;
+  }
+  bool neg = false;
+  const int near0 = from_sat ? L - 1 : 0;
+  double bnear = planck_mod(hvk, tkp[near0]);
+  const bool want_tl = (tau_layer != nullptr) && (tl_angle >= a0) && (tl_angle < a0 + NA);
+  if (want_tl) tau_layer[row] = 0.0;
+
+  for (int step = 0; step < L - 1; ++step) {
+    const int j = from_sat ? (L - 1 - step) : (step + 1);  // layer j spans levels j-1 .. j
+    const int far = from_sat ? j - 1 : j;
+    const double xw = layer_mean(awet[row + j - 1], awet[row + j], true, neg);
+    const double xd = layer_mean(adry[row + j - 1], adry[row + j], true, neg);
+    double xl = 0.0, xi = 0.0;
+    if (CLOUDY) {
+      xl = layer_mean(aliq[row + j - 1], aliq[row + j], false, neg);
+      xi = layer_mean(aice[row + j - 1], aice[row + j], false, neg);
+    }
+    const double bfar = planck_mod(hvk, tkp[far]);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const double dsa = (a0 + a < A) ? dsp[(long long)a * L + j] : 0.0;
+      const double tw = xw * dsa;
+      const double td = xd * dsa;
+      sw[a] += tw;
+      sd[a] += td;
+      double tau = tw + td;
+      if (CLOUDY) {
+        const double tl = xl * dsa;
+        const double ti = xi * dsa;
+        sl[a] += tl;
+        si[a] += ti;
+        tau = tau + ti + tl;
+      }
+      const double ex = exp(-tau);
+      const double boftlay = (bnear + bfar * ex) * rcp_fast(1.0 + ex);
+      batm[a] = fma(boftlay * trans[a], 1.0 - ex, batm[a]);
+      trans[a] *= ex;
+      tauprof[a] += tau;
+      if (want_tl && a0 + a == tl_angle) tau_layer[row + j] = tau;
+    }
+    bnear = bfar;
+  }
+
+  const bool bad = neg || (status && (status[p] & MWRT_ST_NAN_INPUT));  // bit set by earlier kernels
+  if (neg && status) atomicOr(&status[p], MWRT_ST_NEG_ABS);
+  const double bbg = from_sat ? emis * planck_mod(hvk, tkp[0]) : planck_mod(hvk, kTCosmic);
+  const long long obase = idx * (long long)A + a0;
+#pragma unroll
+  for (int a = 0; a < NA; ++a) {
+    if (a0 + a >= A) break;
+    double boftotl, boftmr;
+    if (tauprof[a] < kExpMax) {
+      const double et = exp(-tauprof[a]);
+      boftotl = bbg * et + batm[a];
+      boftmr = batm[a] / (1.0 - et);
+    } else {
+      boftotl = batm[a];
+      boftmr = batm[a];
+    }
+    double o_tot = bright(hvk, boftotl), o_atm = bright(hvk, batm[a]), o_mr = bright(hvk, boftmr);
+    double o_w = sw[a], o_d = sd[a], o_l = sl[a], o_i = si[a];
+    if (bad) o_tot = o_atm = o_mr = o_w = o_d = o_l = o_i = nan("");
+    if (tbtotal) tbtotal[obase + a] = o_tot;
+    if (tbatm) tbatm[obase + a] = o_atm;
+    if (tmr) tmr[obase + a] = o_mr;
+    if (tauwet) tauwet[obase + a] = o_w;
+    if (taudry) taudry[obase + a] = o_d;
+    if (tauliq) tauliq[obase + a] = o_l;
+    if (tauice) tauice[obase + a] = o_i;
+  }
+}
+
+template <int NA>
+static int launch_rte_na(bool cloudy, int P, int L, int F, int A, const double* tk,
+                         const double* awet, const double* adry, const double* aliq,
+                         const double* aice, const double* ds, const double* frq, int from_sat,
+                         double emis, double* tbtotal, double* tbatm, double* tmr, double* tauwet,
+                         double* taudry, double* tauliq, double* tauice, double* tau_layer,
+                         int tl_angle, int* status, cudaStream_t st) {
+  const long long n = (long long)P * F;
+  dim3 grid((unsigned)((n + kRteThreads - 1) / kRteThreads), (unsigned)((A + NA - 1) / NA));
+  if (cloudy)
+    k_rte<NA, true><<<grid, kRteThreads, 0, st>>>(P, L, F, A, tk, awet, adry, aliq, aice, ds, frq,
+                                                  from_sat, emis, tbtotal, tbatm, tmr, tauwet,
+                                                  taudry, tauliq, tauice, tau_layer, tl_angle,
+                                                  status);
+  else
+    k_rte<NA, false><<<grid, kRteThreads, 0, st>>>(P, L, F, A, tk, awet, adry, aliq, aice, ds, frq,
+                                                   from_sat, emis, tbtotal, tbatm, tmr, tauwet,
+                                                   taudry, tauliq, tauice, tau_layer, tl_angle,
+                                                   status);
+  MWRT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int rte_launch(int P, int L, int F, int A, const double* tk, const double* awet, const double* adry,
+               const double* aliq, const double* aice, const double* ds, const double* frq,
+               int from_sat, double emis, double* tbtotal, double* tbatm, double* tmr,
+               double* tauwet, double* taudry, double* tauliq, double* tauice, double* tau_layer,
+               int tl_angle, int* status, cudaStream_t st) {
+  const bool cloudy = (aliq != nullptr) && (aice != nullptr);
+#define MWRT_RTE_ARGS cloudy, P, L, F, A, tk, awet, adry, aliq, aice, ds, frq, from_sat, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, st
+  int na;
+  if (A <= 1) na = 1;
+  else if (A <= 2) na = 2;
+  else if (A <= 4) na = 4;
+  else if (A <= 5) na = 5;
+  else if (A <= 8) na = 8;
+  else if (A <= 10) na = 10;
+  else na = (((A + 9) / 10) * 10 <= ((A + 7) / 8) * 8) ? 10 : 8;
+  switch (na) {
+    case 1: return launch_rte_na<1>(MWRT_RTE_ARGS);
+    case 2: return launch_rte_na<2>(MWRT_RTE_ARGS);
+    case 4: return launch_rte_na<4>(MWRT_RTE_ARGS);
+    case 5: return launch_rte_na<5>(MWRT_RTE_ARGS);
+    case 8: return launch_rte_na<8>(MWRT_RTE_ARGS);
+    default: return launch_rte_na<10>(MWRT_RTE_ARGS);
+  }
+#undef MWRT_RTE_ARGS
+}
+
+// ------------------------------------------------------------------------------------------------
+// Slant path: thread = (profile, angle)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double refr_index(double p, double tk, double e) {
+  const double pa = p - e;
+  const double tc = tk - 273.16;
+  const double tk2 = tk * tk;
+  const double tc2 = tc * tc;
+  const double rza = 1.0 + pa * (5.79e-07 * (1.0 + 0.52 / tk) - 0.00094611 * tc / tk2);
+  const double rzw = 1.0 + 1650.0 * (e / (tk * tk2)) *
+                               (1.0 - 0.01317 * tc + 0.000175 * tc2 + 1.44e-06 * (tc2 * tc));
+  const double wetn = (64.79 * (e / tk) + 377600.0 * (e / tk2)) * rzw;
+  const double dryn = 77.6036 * (pa / tk) * rza;
+  return 1.0 + (dryn + wetn) * 1e-06;
+}
+
+__global__ void k_slant_path(const int P, const int L, const int A, const double* __restrict__ z,
+                             const double* __restrict__ p, const double* __restrict__ tk,
+                             const double* __restrict__ e, const double* __restrict__ angles,
+                             const int ray_tracing, double* __restrict__ ds,
+                             int* __restrict__ status) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)P * A) return;
+  const long long ip = idx / A;
+  const int ia = (int)(idx - ip * A);
+  const double* zp = z + ip * L;
+  double* dsp = ds + idx * (long long)L;
+  const double angle = angles[ia];
+  const double z0 = zp[0];
+  const double pi = 3.141592653589793;
+  bool znan = isnan(z0);
+  dsp[0] = 0.0;
+  if (!ray_tracing) {
+    const double amass = 1.0 / sin(angle * pi / 180.0);
+    double zl = zp[0] - z0;
+    for (int i = 1; i < L; ++i) {
+      const double zi = zp[i] - z0;
+      znan |= isnan(zi);
+      dsp[i] = (zi - zl) * amass;
+      zl = zi;
+    }
+    if (znan && status && ia == 0) atomicOr(&status[ip], MWRT_ST_NAN_INPUT);
+    return;
+  }
+  const double* pp = p + ip * L;
+  const double* tp = tk + ip * L;
+  const double* ep = e + ip * L;
+  // refractive index below 1 anywhere: PyRTlib warns and returns no path
+  bool badn = false;
+  for (int i = 0; i < L; ++i) {
+    znan |= isnan(zp[i]);
+    badn |= (refr_index(pp[i], tp[i], ep[i]) < 1.0);
+  }
+  if (znan && status && ia == 0) atomicOr(&status[ip], MWRT_ST_NAN_INPUT);
+  for (int i = 1; i < L; ++i) dsp[i] = 0.0;
+  if (badn) {
+    if (status) atomicOr(&status[ip], MWRT_ST_DUCTING);
+    return;
+  }
+  if ((angle >= 89.0 && angle <= 91.0) || angle == -90.0) {
+    double zl = zp[0] - z0;
+    for (int i = 1; i < L; ++i) {
+      const double zi = zp[i] - z0;
+      dsp[i] = zi - zl;
+      zl = zi;
+    }
+    return;
+  }
+  const double re = kEarthRadius;
+  const double theta0 = angle * (pi / 180.0);
+  const double zr0 = zp[0] - z0;  // 0 unless NaN
+  const double rs = re + zr0 + z0;
+  const double costh0 = cos(theta0);
+  const double sina = sin(theta0 * 0.5);
+  const double a0 = 2.0 * sina * sina;
+  double phil = 0.0, taul = 0.0, rl = re + zr0 + z0, tanthl = tan(theta0);
+  const double n0 = refr_index(pp[0], tp[0], ep[0]);
+  double nl_ = n0, zl = zr0;
+  for (int i = 1; i < L; ++i) {
+    const double zi = zp[i] - z0;
+    const double ni = refr_index(pp[i], tp[i], ep[i]);
+    const double r = re + zi + z0;
+    double refbar;
+    if (ni == nl_ || ni == 1.0 || nl_ == 1.0)
+      refbar = (ni + nl_) * 0.5;
+    else
+      refbar = 1.0 + (nl_ - ni) / (log((nl_ - 1.0) / (ni - 1.0)));
+    const double argdth = zi / rs - (n0 - ni) * costh0 / ni;
+    const double argth = 0.5 * (a0 + argdth) / r;
+    if (argth <= 0.0) {
+      if (status) atomicOr(&status[ip], MWRT_ST_DUCTING);
+      return;  // ducting: the rest of ds stays 0, like upstream
+    }
+    const double sint = sqrt(r * argth);
+    double theta = 2.0 * asin(sint);
+    double dtheta;
+    if ((theta - 2.0 * theta0) <= 0.0) {
+      const double dendth = 2.0 * (sint + sina) * cos((theta + theta0) * 0.25);
+      const double sind4 = (0.5 * argdth - zi * argth) / dendth;
+      dtheta = 4.0 * asin(sind4);
+      theta = theta0 + dtheta;
+    } else {
+      dtheta = theta - theta0;
+    }
+    const double tanth = tan(theta);
+    const double cthbar = ((1.0 / tanth) + (1.0 / tanthl)) * 0.5;
+    const double dtau = cthbar * (nl_ - ni) / refbar;
+    const double tau = taul + dtau;
+    const double phi = dtheta + tau;
+    const double sh = sin((phi - phil) * 0.5);
+    const double dz = zi - zl;
+    double dsi = sqrt(dz * dz + 4.0 * r * rl * (sh * sh));
+    if (dtau != 0.0) {
+      const double dtaua = fabs(tau - taul);
+      dsi = dsi * (dtaua / (2.0 * sin(dtaua * 0.5)));
+    }
+    dsp[i] = dsi;
+    phil = phi; taul = tau; rl = r; tanthl = tanth; nl_ = ni; zl = zi;
+  }
+}
+
+int slant_path_launch(int P, int L, int A, const double* z, const double* p, const double* tk,
+                      const double* e, const double* angles, int ray_tracing, double* ds, int* status,
+                      cudaStream_t st) {
+  const long long n = (long long)P * A;
+  k_slant_path<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(P, L, A, z, p, tk, e, angles, ray_tracing,
+                                                           ds, status);
+  MWRT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Channel band-pass average (BASELINE.json config 3): fixed summation order -> deterministic
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bandpass(const long long n, const int C, const int S, const int A,
+                           const double* __restrict__ in, const double* __restrict__ w,
+                           double* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (p, c, a)
+  if (idx >= n) return;
+  const int a = (int)(idx % A);
+  const long long pc = idx / A;
+  const int c = (int)(pc % C);
+  const long long p = pc / C;
+  const double* src = in + ((p * C + c) * (long long)S) * A + a;
+  double acc = 0.0;
+  for (int s = 0; s < S; ++s) acc = fma(w ? w[c * S + s] : 1.0 / S, src[(long long)s * A], acc);
+  out[idx] = acc;
+}
+
+int bandpass_launch(int P, int C, int S, int A, const double* in, const double* w, double* out,
+                    cudaStream_t st) {
+  const long long n = (long long)P * C * A;
+  k_bandpass<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, C, S, A, in, w, out);
+  MWRT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mwrt

@@ -1,0 +1,290 @@
+"""Batched forward model: the GPU replacement of `TbCloudRTE(...).execute()` for P profiles at once.
+
+Reference path replaced: the triple loop time x Crop x elevation with four model evaluations each at
+`/root/reference/python_src/proc/PyRTlib_processing.py:99-151`.  All arithmetic runs in libmwrt.so
+(hand-written sm_100a CUDA behind the C ABI of include/mwrt.h); PyTorch is only used for device
+memory, streams and (in `distributed.py`) NCCL.  No CPU fallback.
+
+Conventions (PyRTlib's): profiles ground-first, z [km], p [mb], t [K], rh [fraction], frq [GHz],
+angles [deg elevation]; outputs (P, F, A).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .models import get_model
+
+FIELDS = ("tbtotal", "tbatm", "tmr", "tauwet", "taudry", "tauliq", "tauice")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("mwr_fast_forward_operators_and_lbls_b200 needs a CUDA device (B200, "
+                           "sm_100a); there is no CPU fallback")
+    _lib.set_device(torch.cuda.current_device())
+
+
+def _dev64(x, device=None):
+    """(P,L) fp64 contiguous CUDA tensor from tensor / ndarray, never aliasing-then-mutating input."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64))
+    return t.to(device=device or "cuda", dtype=torch.float64).contiguous()
+
+
+def _host_f64(x):
+    return np.ascontiguousarray(np.atleast_1d(np.asarray(x, dtype=np.float64)))
+
+
+class Plan:
+    """`mwrt_plan`: fixes (model, L, F, A, frq, angles, flags); owns workspace and streams."""
+
+    def __init__(self, model, L, frq, angles, ray_tracing=False, from_sat=False, cloudy=False,
+                 tau_layers=False, chunk_profiles=0, emissivity=1.0, bandpass=None):
+        _need_cuda()
+        self.lib = _lib.load()
+        self.model = get_model(model)
+        self.frq = _host_f64(frq)
+        self.angles = _host_f64(angles)
+        if np.isnan(self.frq).any() or np.isnan(self.angles).any():
+            raise ValueError("NaN in frequencies or angles")  # reference gate, PyRTlib_processing.py:77-78
+        self.L, self.F, self.A = int(L), len(self.frq), len(self.angles)
+        self.flags = ((_lib.F_RAY_TRACING if ray_tracing else 0) | (_lib.F_FROM_SAT if from_sat else 0)
+                      | (_lib.F_CLOUDY if cloudy else 0) | (_lib.F_TAU_LAYERS if tau_layers else 0))
+        self.cloudy, self.tau_layers = bool(cloudy), bool(tau_layers)
+        h = C.c_void_p()
+        _lib.check(self.lib.mwrt_plan_create(self.model.handle, self.L, self.F, self.A,
+                                             self.frq.ctypes.data_as(_lib.c_dp),
+                                             self.angles.ctypes.data_as(_lib.c_dp), self.flags,
+                                             int(chunk_profiles), C.byref(h)), "plan_create")
+        self._h = h
+        self.Fo = self.F
+        if emissivity != 1.0:
+            _lib.check(self.lib.mwrt_plan_set_emissivity(h, float(emissivity)), "set_emissivity")
+        if bandpass is not None:
+            nchan, nsub, w = bandpass
+            wp = None
+            if w is not None:
+                w = np.ascontiguousarray(w, dtype=np.float64).reshape(nchan, nsub)
+                wp = w.ctypes.data_as(_lib.c_dp)
+            _lib.check(self.lib.mwrt_plan_set_bandpass(h, int(nchan), int(nsub), wp), "set_bandpass")
+            self.Fo = int(nchan)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self.lib.mwrt_plan_destroy(h)
+            except Exception:
+                pass
+
+    def launch_count(self, P):
+        return int(self.lib.mwrt_plan_launch_count(self._h, int(P)))
+
+    # ---- device buffers in, device buffers out ------------------------------------------------
+    def forward(self, z, p, t, rh, denliq=None, denice=None, fields=FIELDS, out=None):
+        """All arguments (P,L) CUDA fp64 tensors.  Returns dict of (P,Fo,A) CUDA tensors
+        (+ 'tau_layer' (P,F,L) if the plan was made with tau_layers, + 'status' (P,) int32).
+        Asynchronous on the current torch stream."""
+        P = z.shape[0]
+        for x in (z, p, t, rh):
+            if not (x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
+                    and tuple(x.shape) == (P, self.L)):
+                raise ValueError("inputs must be contiguous CUDA fp64 tensors of shape (P,%d)" % self.L)
+        dev = z.device
+        res = out if out is not None else {}
+        for f in fields:
+            if f not in res:
+                res[f] = torch.empty((P, self.Fo, self.A), dtype=torch.float64, device=dev)
+        if self.tau_layers and "tau_layer" not in res:
+            res["tau_layer"] = torch.empty((P, self.F, self.L), dtype=torch.float64, device=dev)
+        if "status" not in res:
+            res["status"] = torch.empty((P,), dtype=torch.int32, device=dev)
+        pin = _lib.Profiles(_ptr(z), _ptr(p), _ptr(t), _ptr(rh),
+                            _ptr(denliq if self.cloudy else None), _ptr(denice if self.cloudy else None))
+        pout = _lib.Outputs(*[_ptr(res.get(f)) for f in FIELDS], _ptr(res.get("tau_layer")),
+                            _ptr(res["status"]))
+        with torch.cuda.device(dev):
+            _lib.set_device(dev.index if dev.index is not None else torch.cuda.current_device())
+            _lib.check(self.lib.mwrt_plan_forward_device(self._h, int(P), C.byref(pin), C.byref(pout),
+                                                         _stream()), "forward_device")
+        return res
+
+    # ---- host buffers in, host buffers out (chunked copy/compute overlap inside the library) ---
+    def forward_host(self, z, p, t, rh, denliq=None, denice=None, fields=FIELDS, out=None):
+        """All arguments (P,L) host fp64 arrays (numpy or CPU torch; pinned memory makes the copies
+        asynchronous).  Returns dict of numpy arrays; blocks until the results are in host memory."""
+        def as_np(x):
+            if x is None:
+                return None
+            if isinstance(x, torch.Tensor):
+                x = x.numpy()
+            return np.ascontiguousarray(x, dtype=np.float64)
+        z, p, t, rh, denliq, denice = (as_np(v) for v in (z, p, t, rh, denliq, denice))
+        P = z.shape[0]
+        for x in (z, p, t, rh):
+            if x.shape != (P, self.L):
+                raise ValueError("inputs must have shape (P,%d)" % self.L)
+        res = out if out is not None else {}
+        for f in fields:
+            if f not in res:
+                res[f] = np.empty((P, self.Fo, self.A), dtype=np.float64)
+        if self.tau_layers and "tau_layer" not in res:
+            res["tau_layer"] = np.empty((P, self.F, self.L), dtype=np.float64)
+        if "status" not in res:
+            res["status"] = np.empty((P,), dtype=np.int32)
+
+        def hp(x):
+            if x is None:
+                return C.c_void_p(None)
+            if isinstance(x, torch.Tensor):
+                return C.c_void_p(x.data_ptr())
+            return C.c_void_p(x.ctypes.data)
+        pin = _lib.Profiles(hp(z), hp(p), hp(t), hp(rh), hp(denliq if self.cloudy else None),
+                            hp(denice if self.cloudy else None))
+        pout = _lib.Outputs(*[hp(res.get(f)) for f in FIELDS], hp(res.get("tau_layer")), hp(res["status"]))
+        _lib.set_device(torch.cuda.current_device())
+        _lib.check(self.lib.mwrt_plan_forward_host(self._h, int(P), C.byref(pin), C.byref(pout)),
+                   "forward_host")
+        return res
+
+
+def simulate(z, p, t, rh, frq, angles, model, ray_tracing=False, from_sat=False, denliq=None,
+             denice=None, fields=FIELDS, tau_layers=False, bandpass=None, device=None):
+    """One-call batched forward model (SURVEY.md 8(b) "batched entry").
+
+    z,p,t,rh[,denliq,denice]: (P,L) arrays/tensors, ground-first.  Returns dict of (P,F,A) CUDA
+    tensors.  A profile containing NaN gives NaN outputs (status bit 1) and the batch continues --
+    the reference's per-profile gate at PyRTlib_processing.py:117-119,153-154."""
+    _need_cuda()
+    zt = _dev64(z, device)
+    cloudy = denliq is not None or denice is not None
+    if cloudy:
+        denliq = torch.zeros_like(zt) if denliq is None else _dev64(denliq, zt.device)
+        denice = torch.zeros_like(zt) if denice is None else _dev64(denice, zt.device)
+    plan = Plan(model, zt.shape[1], frq, angles, ray_tracing=ray_tracing, from_sat=from_sat,
+                cloudy=cloudy, tau_layers=tau_layers, bandpass=bandpass)
+    res = plan.forward(zt, _dev64(p, zt.device), _dev64(t, zt.device), _dev64(rh, zt.device),
+                       denliq, denice, fields=fields)
+    torch.cuda.current_stream().synchronize()  # the plan (and its workspace) dies with this frame
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
+# stage entry points (used by the parity tests: absorption / optical depth at 1e-9, TB at 1e-3 K)
+# ------------------------------------------------------------------------------------------------
+def vapor(t, rh):
+    """RTEquation.vapor on device: returns e [mb], rho [g m^-3]."""
+    _need_cuda()
+    lib = _lib.load()
+    t, rh = _dev64(t), _dev64(rh)
+    e, rho = torch.empty_like(t), torch.empty_like(t)
+    _lib.check(lib.mwrt_vapor_f64(t.numel(), _ptr(t), _ptr(rh), _ptr(e), _ptr(rho), _stream()), "vapor")
+    return e, rho
+
+
+def absorption(model, p, t, e, frq, denliq=None, denice=None):
+    """awet, adry[, aliq, aice] as (P,F,L) CUDA tensors + status (P,)."""
+    _need_cuda()
+    lib = _lib.load()
+    m = get_model(model)
+    p, t, e = _dev64(p), _dev64(t), _dev64(e)
+    P, L = p.shape
+    f = torch.from_numpy(_host_f64(frq)).cuda()
+    F = f.numel()
+    awet = torch.empty((P, F, L), dtype=torch.float64, device="cuda")
+    adry = torch.empty_like(awet)
+    cloudy = denliq is not None or denice is not None
+    aliq = aice = None
+    if cloudy:
+        denliq = torch.zeros_like(p) if denliq is None else _dev64(denliq)
+        denice = torch.zeros_like(p) if denice is None else _dev64(denice)
+        aliq, aice = torch.empty_like(awet), torch.empty_like(awet)
+    status = torch.zeros((P,), dtype=torch.int32, device="cuda")
+    _lib.check(lib.mwrt_absorption_f64(m.handle, P, L, F, _ptr(p), _ptr(t), _ptr(e), _ptr(denliq),
+                                       _ptr(denice), _ptr(f), _ptr(awet), _ptr(adry), _ptr(aliq),
+                                       _ptr(aice), _ptr(status), _stream()), "absorption")
+    torch.cuda.current_stream().synchronize()
+    return dict(awet=awet, adry=adry, aliq=aliq, aice=aice, status=status)
+
+
+def slant_path(z, p, t, e, angles, ray_tracing=False):
+    """ds (P,A,L) [km] + status."""
+    _need_cuda()
+    lib = _lib.load()
+    z = _dev64(z)
+    P, L = z.shape
+    a = torch.from_numpy(_host_f64(angles)).cuda()
+    A = a.numel()
+    p = _dev64(p) if p is not None else None
+    t = _dev64(t) if t is not None else None
+    e = _dev64(e) if e is not None else None
+    ds = torch.empty((P, A, L), dtype=torch.float64, device="cuda")
+    status = torch.zeros((P,), dtype=torch.int32, device="cuda")
+    _lib.check(lib.mwrt_slant_path_f64(P, L, A, _ptr(z), _ptr(p), _ptr(t), _ptr(e), _ptr(a),
+                                       int(bool(ray_tracing)), _ptr(ds), _ptr(status), _stream()),
+               "slant_path")
+    torch.cuda.current_stream().synchronize()
+    return ds, status
+
+
+def rte(t, awet, adry, ds, frq, aliq=None, aice=None, from_sat=False, emissivity=1.0,
+        tau_layer_angle=None):
+    """Layer integration + RTE from given absorption and path: dict of (P,F,A) tensors."""
+    _need_cuda()
+    lib = _lib.load()
+    t = _dev64(t)
+    P, F, L = awet.shape
+    A = ds.shape[1]
+    f = torch.from_numpy(_host_f64(frq)).cuda()
+    res = {k: torch.empty((P, F, A), dtype=torch.float64, device="cuda") for k in FIELDS}
+    tl = None
+    if tau_layer_angle is not None:
+        tl = torch.empty((P, F, L), dtype=torch.float64, device="cuda")
+        res["tau_layer"] = tl
+    status = torch.zeros((P,), dtype=torch.int32, device="cuda")
+    res["status"] = status
+    _lib.check(lib.mwrt_rte_f64(P, L, F, A, _ptr(t), _ptr(awet), _ptr(adry), _ptr(aliq), _ptr(aice),
+                                _ptr(ds), _ptr(f), int(bool(from_sat)), float(emissivity),
+                                *[_ptr(res[k]) for k in FIELDS], _ptr(tl),
+                                int(tau_layer_angle or 0), _ptr(status), _stream()), "rte")
+    torch.cuda.current_stream().synchronize()
+    return res
+
+
+def bandpass(x, nchan, nsub, weights=None):
+    """(P, nchan*nsub, A) -> (P, nchan, A) weighted channel average."""
+    _need_cuda()
+    lib = _lib.load()
+    x = x.contiguous()
+    P, F, A = x.shape
+    if F != nchan * nsub:
+        raise ValueError("nchan*nsub must equal the frequency axis")
+    w = None
+    if weights is not None:
+        w = torch.from_numpy(np.ascontiguousarray(weights, dtype=np.float64).reshape(nchan, nsub)).cuda()
+    out = torch.empty((P, nchan, A), dtype=torch.float64, device="cuda")
+    _lib.check(lib.mwrt_bandpass_f64(P, nchan, nsub, A, _ptr(x), _ptr(w), _ptr(out), _stream()),
+               "bandpass")
+    torch.cuda.current_stream().synchronize()
+    return out
+
+
+def measure_dfma_peak():
+    """(fp64 FLOP/s of a DFMA stream, SM clock estimate in MHz) measured on the current device."""
+    _need_cuda()
+    lib = _lib.load()
+    fl, mhz = C.c_double(), C.c_double()
+    _lib.check(lib.mwrt_measure_dfma_peak(C.byref(fl), C.byref(mhz)), "measure_dfma_peak")
+    return fl.value, mhz.value

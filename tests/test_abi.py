@@ -1,0 +1,112 @@
+"""No-GPU checks of the drop-in boundary: libmwrt.so builds for sm_100a, loads, and exports every
+symbol include/mwrt.h declares; host-side logic that needs no device."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mwrt.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mwrt_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(built_lib):
+    from mwr_fast_forward_operators_and_lbls_b200 import _lib
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    lib = C.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), "libmwrt.so does not export %s" % name
+    # and the Python binding knows every one of them
+    assert sorted(_lib.SYMBOLS) == declared
+
+
+def test_library_is_sm100a_native(built_lib):
+    out = subprocess.run(["cuobjdump", "-lelf", built_lib], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_builtin_models_match_json_descriptors(built_lib):
+    """The tables compiled into the .so are the JSON descriptors the oracle reads."""
+    from mwr_fast_forward_operators_and_lbls_b200 import _lib, models
+    lib = _lib.load()
+    assert lib.mwrt_version() >= 100
+    names = models.implemented_models()
+    for m in models.REFERENCE_MODELS + ("R22SD",):
+        assert m in names
+    for name in names:
+        d = _lib.ModelDesc()
+        assert lib.mwrt_builtin_model_desc(name.encode(), C.byref(d)) == 0
+        js = models.load_descriptor(name)
+        assert d.n_h2o == len(js["h2o"]["fl"]) and d.n_o2 == len(js["o2"]["f"])
+        h = np.ctypeslib.as_array(d.h2o_lines, shape=(len(_lib.H2O_COLS), d.n_h2o))
+        o = np.ctypeslib.as_array(d.o2_lines, shape=(len(_lib.O2_COLS), d.n_o2))
+        for i, c in enumerate(_lib.H2O_COLS):
+            assert np.array_equal(h[i], np.array(js["h2o"][c])), (name, c)
+        for i, c in enumerate(_lib.O2_COLS):
+            assert np.array_equal(o[i], np.array(js["o2"][c])), (name, c)
+        assert d.h2o_cf == js["h2o"]["cf"] and d.o2_iso == js["o2"]["iso"] and d.n2_m == js["n2"]["m"]
+        assert d.o2_mixing == js["o2"]["mixing"] and bool(d.h2o_sd) == js["h2o"]["sd"]
+
+
+def test_unknown_model_is_a_value_error(built_lib):
+    from mwr_fast_forward_operators_and_lbls_b200 import _lib
+    lib = _lib.load()
+    d = _lib.ModelDesc()
+    rc = lib.mwrt_builtin_model_desc(b"R99", C.byref(d))
+    assert rc == _lib.E_MODEL
+    with pytest.raises(ValueError):
+        _lib.check(rc, "init_absmdl")
+    assert b"R99" in lib.mwrt_last_error()
+
+
+def test_no_cpu_fallback_without_gpu(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import mwr_fast_forward_operators_and_lbls_b200 as pkg
+    d = pkg.synth_profiles(2, 20)
+    with pytest.raises(RuntimeError):
+        pkg.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, [90.0], "R98")
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "mwr_fast_forward_operators_and_lbls_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_synth_profiles_realism_windows():
+    """Windows of preprocessing4all.py:553-572."""
+    import mwr_fast_forward_operators_and_lbls_b200 as pkg
+    d = pkg.synth_profiles(200, 100, seed=1234, clouds=True)
+    assert d["z"].shape == (200, 100)
+    assert np.all(np.diff(d["z"], axis=1) > 0) and np.all(np.diff(d["p"], axis=1) < 0)
+    assert d["p"].max() < 1100 and d["p"].min() > 0
+    assert d["t"].min() > 150 and d["t"].max() < 400
+    assert d["rh"].min() >= 0.0 and d["rh"].max() <= 1.1
+    assert d["denliq"].max() <= 0.5 and (d["denliq"] > 0).any()
+    d2 = pkg.synth_profiles(200, 100, seed=1234, clouds=True)
+    assert all(np.array_equal(d[k], d2[k]) for k in d)
+    icon = pkg.synth_profiles(4, 65, seed=1, top_km=22.0, exponent=2.5, lowest_layer_km=0.02)
+    assert abs((icon["z"][:, 1] - icon["z"][:, 0]).mean() - 0.02) < 0.005
+    f = pkg.band_frequencies(50)
+    assert f.shape == (700,) and abs(f[:50].mean() - 22.24) < 1e-9
+    assert pkg.dense_spectrum().shape == (4001,)
+
+
+def test_golden_file_is_labelled_unpinned():
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "config1_us_standard.json")))
+    assert "NOT PyRTlib" in g["source"]

@@ -1,0 +1,347 @@
+"""GPU parity tests: the CUDA path (through the C ABI of include/mwrt.h) against the CPU oracle on the
+same seeded inputs.  Tolerances are the ones BASELINE.json:north_star states:
+  fp64 absorption coefficients and optical depths within 1e-9 relative, TB within 1e-3 K.
+The oracle is the in-repo restatement (parity with real PyRTlib is unpinned).
+"""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-9      # absorption / optical depth, relative (north_star)
+TB_ABS = 1e-3   # brightness temperature, K (north_star)
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "config1_us_standard.json")
+
+
+@pytest.fixture(scope="module")
+def pkg(built_lib):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import mwr_fast_forward_operators_and_lbls_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def ora():
+    from oracle import atmospheres, pyrtlib_scalar, pyrtlib_vec
+    class O:  # noqa: E306
+        atm, ps, pv = atmospheres, pyrtlib_scalar, pyrtlib_vec
+    return O
+
+
+def rel_err(a, b, floor=0.0):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor + 1e-300)))
+
+
+def cpu(x):
+    return x.detach().cpu().numpy()
+
+
+ALL_MODELS = ["R98", "R03", "R16", "R17", "R19", "R19SD", "R20", "R20SD", "R21SD", "R22SD", "R23",
+              "R23SD", "R24"]
+
+
+def test_native_library_loaded(pkg):
+    """The extension in use is the in-tree libmwrt.so (no eager/CPU fallback exists)."""
+    from mwr_fast_forward_operators_and_lbls_b200 import _lib
+    maps = open("/proc/self/maps").read()
+    _lib.load()
+    assert "libmwrt.so" in open("/proc/self/maps").read() or "libmwrt.so" in maps
+
+
+def test_vapor(pkg, ora):
+    d = pkg.synth_profiles(64, 100, seed=3)
+    e, rho = pkg.vapor(d["t"], d["rh"])
+    e0, rho0 = ora.pv.vapor(d["t"], d["rh"])
+    assert rel_err(cpu(e), e0) < 1e-13
+    assert rel_err(cpu(rho), rho0) < 1e-13
+
+
+@pytest.mark.parametrize("mdl", ALL_MODELS)
+def test_absorption_hatpro_channels(pkg, ora, mdl):
+    """awet/adry at the 14 HATPRO channels, every model string, 1e-9 relative."""
+    d = pkg.synth_profiles(48, 100, seed=11)
+    e, _ = ora.pv.vapor(d["t"], d["rh"])
+    g = pkg.absorption(mdl, d["p"], d["t"], e, pkg.HATPRO_FRQ)
+    awet, adry, _, _ = ora.pv.absorption(mdl, d["p"], d["t"], e, pkg.HATPRO_FRQ)
+    assert rel_err(cpu(g["awet"]), awet) < REL
+    assert rel_err(cpu(g["adry"]), adry) < REL
+    assert int(g["status"].sum()) == 0
+
+
+@pytest.mark.parametrize("mdl", ["R98", "R17", "R20SD", "R24"])
+def test_absorption_wide_spectrum(pkg, ora, mdl):
+    """1-1000 GHz sweep: exercises the 750 GHz cutoffs, line centres, the speed-dependent 22/183 GHz
+    and 118 GHz shapes, the tail frequency block (F=37 is not a multiple of 16)."""
+    d = pkg.synth_profiles(6, 60, seed=5)
+    e, _ = ora.pv.vapor(d["t"], d["rh"])
+    frq = np.concatenate([np.linspace(1.0, 1000.0, 25), [22.235, 118.7503, 183.31, 60.3061, 556.936,
+                                                        752.0332, 916.1712, 50.0, 89.0, 150.0, 325.1529,
+                                                        2.0]])
+    assert len(frq) == 37
+    g = pkg.absorption(mdl, d["p"], d["t"], e, frq)
+    awet, adry, _, _ = ora.pv.absorption(mdl, d["p"], d["t"], e, frq)
+    assert rel_err(cpu(g["awet"]), awet) < REL
+    assert rel_err(cpu(g["adry"]), adry) < REL
+
+
+def test_absorption_custom_model_all_terms(pkg, ora):
+    """Every table column non-zero (perturbed R22SD): shift terms, aair/aself, d2, g/dnu ..."""
+    rng = np.random.default_rng(0)
+    desc = copy.deepcopy(pkg.load_descriptor("R22SD"))
+    desc["name"] = "perturbed"
+    n = len(desc["h2o"]["fl"])
+    for col, scale in (("sr", 1e-3), ("xh", 1.0), ("xhs", 1.0), ("aair", 0.5), ("aself", 0.5),
+                       ("d2", 2e-5), ("d2s", 2e-4), ("sh", 1e-4), ("shs", 1e-3)):
+        desc["h2o"][col] = (np.array(desc["h2o"][col]) + scale * rng.uniform(0.1, 1.0, n)).tolist()
+    desc["h2o"]["w2"] = (np.array(desc["h2o"]["w2"]) + 2e-4 * (rng.uniform(0, 1, n) < 0.4)).tolist()
+    m = len(desc["o2"]["f"])
+    for col in ("g0", "g1", "dnu0", "dnu1"):
+        desc["o2"][col] = (np.array(desc["o2"][col]) + 1e-3 * rng.uniform(-1, 1, m)).tolist()
+    d = pkg.synth_profiles(8, 80, seed=21)
+    e, _ = ora.pv.vapor(d["t"], d["rh"])
+    frq = np.concatenate([pkg.HATPRO_FRQ, [118.0, 118.75, 183.0, 183.31, 321.0, 380.2]])
+    g = pkg.absorption(desc, d["p"], d["t"], e, frq)
+    awet, adry, _, _ = ora.pv.absorption(desc, d["p"], d["t"], e, frq)
+    assert rel_err(cpu(g["awet"]), awet) < REL
+    assert rel_err(cpu(g["adry"]), adry) < REL
+
+
+@pytest.mark.parametrize("mdl", ["R98", "R24"])
+def test_cloud_absorption(pkg, ora, mdl):
+    d = pkg.synth_profiles(64, 100, seed=9, clouds=True)
+    d["denice"][:, 40:43] = 0.03
+    e, _ = ora.pv.vapor(d["t"], d["rh"])
+    frq = np.array([22.24, 31.4, 58.0, 90.0, 150.0])
+    g = pkg.absorption(mdl, d["p"], d["t"], e, frq, d["denliq"], d["denice"])
+    _, _, aliq, aice = ora.pv.absorption(mdl, d["p"], d["t"], e, frq, d["denliq"], d["denice"])
+    assert (aliq > 0).any()
+    assert rel_err(cpu(g["aliq"]), aliq) < REL
+    assert rel_err(cpu(g["aice"]), aice) < REL
+
+
+@pytest.mark.parametrize("rt", [False, True])
+def test_slant_path(pkg, ora, rt):
+    d = pkg.synth_profiles(32, 100, seed=13)
+    e, _ = ora.pv.vapor(d["t"], d["rh"])
+    ang = np.concatenate([pkg.HATPRO_ELEV, [89.5, 1.0, 45.0]])
+    ds, st = pkg.slant_path(d["z"], d["p"], d["t"], e, ang, rt)
+    ds0 = ora.pv.slant_path(d["z"], d["p"], d["t"], e, ang, rt)
+    assert rel_err(cpu(ds)[:, :, 1:], ds0[:, :, 1:]) < REL
+    assert np.all(cpu(ds)[:, :, 0] == 0.0)
+
+
+@pytest.mark.parametrize("from_sat", [False, True])
+def test_rte_stage(pkg, ora, from_sat):
+    """exponential_integration + planck + bright from the ORACLE's absorption: isolates kernel 3."""
+    import torch
+    d = pkg.synth_profiles(24, 100, seed=17)
+    e, _ = ora.pv.vapor(d["t"], d["rh"])
+    awet, adry, _, _ = ora.pv.absorption("R19", d["p"], d["t"], e, pkg.HATPRO_FRQ)
+    ds = ora.pv.slant_path(d["z"], d["p"], d["t"], e, pkg.HATPRO_ELEV, False)
+    g = pkg.rte(d["t"], torch.from_numpy(awet).cuda(), torch.from_numpy(adry).cuda(),
+                torch.from_numpy(ds).cuda(), pkg.HATPRO_FRQ, from_sat=from_sat, tau_layer_angle=3)
+    ref = ora.pv.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, "R19",
+                          from_sat=from_sat, return_layers=True)
+    for k in ("tauwet", "taudry"):
+        assert rel_err(cpu(g[k]), ref[k]) < REL, k
+    assert rel_err(cpu(g["tau_layer"])[:, :, 1:], ref["tau_layer"][:, :, 3, 1:]) < REL
+    for k in ("tbtotal", "tbatm", "tmr"):
+        assert np.max(np.abs(cpu(g[k]) - ref[k])) < TB_ABS, k
+
+
+@pytest.mark.parametrize("mdl", ["R98", "R17", "R20", "R24", "R22SD"])
+@pytest.mark.parametrize("rt", [False, True])
+def test_end_to_end_config2_shape(pkg, ora, mdl, rt):
+    """BASELINE.json config 2 at oracle-sized P: 100 levels x 14 channels x 10 elevations."""
+    d = pkg.synth_profiles(96, 100, seed=1234)
+    out = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, mdl,
+                       ray_tracing=rt)
+    ref = ora.pv.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, mdl,
+                          ray_tracing=rt)
+    for k in ("tauwet", "taudry"):
+        assert rel_err(cpu(out[k]), ref[k]) < REL, k
+    for k in ("tbtotal", "tbatm", "tmr"):
+        err = np.max(np.abs(cpu(out[k]) - ref[k]))
+        assert err < TB_ABS, (k, err)
+    assert int(out["status"].sum()) == 0
+
+
+def test_golden_config1(pkg):
+    """BASELINE.json config 1 against the committed vectors (generated by tests/golden/make_golden.py)."""
+    g = json.load(open(GOLD))
+    z, p, t, rh = (np.array(g[k]) for k in ("z", "p", "t", "rh"))
+    frq, ang = np.array(g["frq"]), np.array(g["angles"])
+    for case in g["cases"]:
+        out = pkg.simulate(z[None], p[None], t[None], rh[None], frq, ang, case["model"],
+                           ray_tracing=case["ray_tracing"])
+        for k in ("tbtotal", "tbatm", "tmr"):
+            a = np.array(case[k]).reshape(len(ang), len(frq)).T
+            assert np.max(np.abs(cpu(out[k])[0] - a)) < TB_ABS, (case["model"], k)
+        for k in ("tauwet", "taudry"):
+            a = np.array(case[k]).reshape(len(ang), len(frq)).T
+            assert rel_err(cpu(out[k])[0], a) < REL, (case["model"], k)
+
+
+def test_tbcloudrte_class_matches_scalar_oracle(pkg, ora):
+    """The reference's exact call pattern (PyRTlib_processing.py:123-127): top-first arrays flipped
+    with [::-1], ONE angle per object, tbtotal column of the DataFrame."""
+    z, p, t, rh = ora.atm.us_standard()
+    z_in, p_in, t_in, rh_in = z[::-1].copy(), p[::-1].copy(), t[::-1].copy(), rh[::-1].copy()
+    keep = [v.copy() for v in (z_in, p_in, t_in, rh_in)]
+    frqs = pkg.HATPRO_FRQ
+    for elevation in (90.0, 5.4):
+        ang = np.array([elevation])
+        for mdl in ("R20", "R24", "R17", "R98"):
+            rte = pkg.TbCloudRTE(z_in[::-1], p_in[::-1], t_in[::-1], rh_in[::-1], frqs, ang)
+            rte.init_absmdl(mdl)
+            rte.satellite = False
+            df = rte.execute()
+            o = ora.ps.TbCloudRTE(z_in[::-1], p_in[::-1], t_in[::-1], rh_in[::-1], frqs, ang)
+            o.init_absmdl(mdl)
+            o.satellite = False
+            ref = o.execute()
+            assert list(df.columns[:8]) == ["tbtotal", "tbatm", "tmr", "tmrcld", "tauwet", "taudry",
+                                            "tauliq", "tauice"]
+            assert np.max(np.abs(df["tbtotal"].values - ref["tbtotal"])) < TB_ABS
+            assert rel_err(df["tauwet"].values, ref["tauwet"]) < REL
+            assert rte.cloudy is False
+    for a, b in zip(keep, (z_in, p_in, t_in, rh_in)):
+        assert np.array_equal(a, b)  # inputs never modified
+    # multi-angle object: DataFrame rows are angle-major, frequency fastest
+    rte = pkg.TbCloudRTE(z, p, t, rh, frqs, pkg.HATPRO_ELEV, absmdl="R24", from_sat=False)
+    df = rte.execute()
+    assert len(df) == 140 and df["angle"].values[13] == 90.0 and df["angle"].values[14] == 30.0
+    assert df["frq"].values[15] == frqs[1]
+    with pytest.raises(ValueError):
+        pkg.TbCloudRTE(z, p, t, rh, frqs, [90.0]).init_absmdl("R99")
+    with pytest.raises(ValueError):
+        pkg.TbCloudRTE(z, p, t, rh, frqs, [90.0]).execute()
+
+
+def test_cloudy_end_to_end_and_class(pkg, ora):
+    d = pkg.synth_profiles(40, 100, seed=77, clouds=True)
+    out = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, "R24",
+                       denliq=d["denliq"], denice=d["denice"])
+    ref = ora.pv.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, "R24",
+                          denliq=d["denliq"], denice=d["denice"])
+    assert (ref["tauliq"] > 0).any()
+    assert rel_err(cpu(out["tauliq"]), ref["tauliq"], floor=1e-30) < REL
+    assert np.max(np.abs(cpu(out["tbtotal"]) - ref["tbtotal"])) < TB_ABS
+    i = int(np.argmax(d["denliq"].max(axis=1)))
+    rte = pkg.TbCloudRTE(d["z"][i], d["p"][i], d["t"][i], d["rh"][i], pkg.HATPRO_FRQ, [90.0, 30.0],
+                         from_sat=False)
+    rte.init_absmdl("R24")
+    rte.init_cloudy(np.array([[1.0], [2.0]]), d["denice"][i], d["denliq"][i])
+    df = rte.execute()
+    assert np.max(np.abs(df["tbtotal"].values.reshape(2, 14).T - ref["tbtotal"][i][:, :2])) < TB_ABS
+    assert (df["tauliq"].values > 0).all()
+
+
+def test_nan_gate_per_profile(pkg, ora):
+    """NaN in -> NaN out for that profile only (PyRTlib_processing.py:71-79,117-119,153-154)."""
+    d = pkg.synth_profiles(16, 50, seed=2)
+    good = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV[:3], "R98")
+    for j, key in enumerate(("z", "p", "t", "rh")):
+        d[key][3 + j, 10 + j] = np.nan
+    out = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV[:3], "R98")
+    st = cpu(out["status"])
+    for i in range(16):
+        bad = 3 <= i <= 6
+        for k in pkg.FIELDS:
+            if k in ("tauliq", "tauice") and not bad:
+                continue
+            v = cpu(out[k])[i]
+            assert np.isnan(v).all() if bad else np.array_equal(v, cpu(good[k])[i]), (i, k)
+        assert bool(st[i] & 1) == bad
+
+
+def test_negative_absorption_flag_and_value_error(pkg):
+    import torch
+    d = pkg.synth_profiles(2, 20, seed=4)
+    awet = torch.full((2, 3, 20), 1e-3, dtype=torch.float64, device="cuda")
+    adry = awet.clone()
+    adry[1, 2, 5] = -1.0
+    ds = torch.ones((2, 1, 20), dtype=torch.float64, device="cuda")
+    g = pkg.rte(d["t"], awet, adry, ds, [22.24, 31.4, 58.0])
+    st = cpu(g["status"])
+    assert st[0] == 0 and st[1] & 2
+    assert np.isnan(cpu(g["tbtotal"])[1, 2]).all() and np.isfinite(cpu(g["tbtotal"])[0]).all()
+
+
+def test_bandpass_fused_plan(pkg, ora):
+    """BASELINE.json config 3 shape: sub-frequencies x top-hat average -> channels."""
+    d = pkg.synth_profiles(12, 100, seed=8, clouds=True)
+    nsub = 5
+    frq = pkg.band_frequencies(nsub)
+    mono = ora.pv.simulate(d["z"], d["p"], d["t"], d["rh"], frq, pkg.HATPRO_ELEV, "R24",
+                           denliq=d["denliq"], denice=d["denice"])
+    ref = mono["tbtotal"].reshape(12, 14, nsub, 10).mean(axis=2)
+    out = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], frq, pkg.HATPRO_ELEV, "R24", denliq=d["denliq"],
+                       denice=d["denice"], bandpass=(14, nsub, None))
+    assert tuple(out["tbtotal"].shape) == (12, 14, 10)
+    assert np.max(np.abs(cpu(out["tbtotal"]) - ref)) < TB_ABS
+    w = np.tile(np.array([0.1, 0.2, 0.4, 0.2, 0.1]), (14, 1))
+    out = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], frq, pkg.HATPRO_ELEV, "R24", denliq=d["denliq"],
+                       denice=d["denice"], bandpass=(14, nsub, w))
+    ref = (mono["tbtotal"].reshape(12, 14, nsub, 10) * w[None, :, :, None]).sum(axis=2)
+    assert np.max(np.abs(cpu(out["tbtotal"]) - ref)) < TB_ABS
+
+
+def test_host_entry_equals_device_entry_and_chunks(pkg):
+    """mwrt_plan_forward_host (chunked H2D/compute/D2H pipeline) == device entry, bit for bit;
+    ragged last chunk; tau_layer output."""
+    import torch
+    d = pkg.synth_profiles(5000, 40, seed=6)
+    plan = pkg.Plan("R17", 40, pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, tau_layers=True, chunk_profiles=1536)
+    dev = plan.forward(*(torch.from_numpy(d[k]).cuda() for k in ("z", "p", "t", "rh")))
+    torch.cuda.synchronize()
+    host = plan.forward_host(d["z"], d["p"], d["t"], d["rh"])
+    for k in pkg.FIELDS + ("tau_layer", "status"):
+        assert np.array_equal(cpu(dev[k]), host[k], equal_nan=True), k
+    assert plan.launch_count(5000) == 4 * 3
+
+
+def test_large_batch_properties(pkg):
+    """Full config-2 size (10^4 x 100 x 14 x 10): size-independent properties instead of the oracle."""
+    d = pkg.synth_profiles(10000, 100, seed=1234)
+    out = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, "R24")
+    tb, tbatm, tmr = cpu(out["tbtotal"]), cpu(out["tbatm"]), cpu(out["tmr"])
+    assert np.isfinite(tb).all()
+    tmax = d["t"].max(axis=1)[:, None, None]
+    tmin = d["t"].min(axis=1)[:, None, None]
+    assert np.all(tb > 2.7) and np.all(tb <= tmax + 1e-6)
+    assert np.all(tbatm <= tb + 1e-9)
+    assert np.all(tmr >= tmin - 1e-6) and np.all(tmr <= tmax + 1e-6)
+    am = 1.0 / np.sin(np.deg2rad(pkg.HATPRO_ELEV))
+    tw = cpu(out["tauwet"])
+    assert rel_err(tw, tw[:, :, :1] * am[None, None, :]) < 1e-12
+    assert np.all(np.diff(tb[:, :7, :], axis=2) > 0)      # K band: TB rises towards the horizon
+    # batch invariance: a profile's result does not depend on its neighbours
+    sub = pkg.simulate(d["z"][4000:4010], d["p"][4000:4010], d["t"][4000:4010], d["rh"][4000:4010],
+                       pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, "R24")
+    assert np.array_equal(cpu(sub["tbtotal"]), tb[4000:4010])
+
+
+def test_dense_spectrum_and_icon_shapes(pkg, ora):
+    """Config 4 (dense 20-60 GHz, 150 levels, per-layer tau) and config 5 (65 levels) at small P."""
+    frq = pkg.dense_spectrum()[::40]       # 101 frequencies -> tail block of the 16-wide kernel
+    d = pkg.synth_profiles(6, 150, seed=31)
+    out = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], frq, [90.0], "R24", tau_layers=True)
+    ref = ora.pv.simulate(d["z"], d["p"], d["t"], d["rh"], frq, [90.0], "R24", return_layers=True)
+    assert rel_err(cpu(out["tau_layer"])[:, :, 1:], ref["tau_layer"][:, :, 0, 1:]) < REL
+    assert np.max(np.abs(cpu(out["tbtotal"]) - ref["tbtotal"])) < TB_ABS
+    d = pkg.synth_profiles(32, 65, seed=32, top_km=22.0, exponent=2.5, lowest_layer_km=0.02)
+    out = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, "R20")
+    ref = ora.pv.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, "R20")
+    assert np.max(np.abs(cpu(out["tbtotal"]) - ref["tbtotal"])) < TB_ABS
+
+
+def test_dfma_peak_is_plausible(pkg):
+    fl, mhz = pkg.measure_dfma_peak()
+    assert 5e12 < fl < 6e13, fl      # B200 nominal 37.2 TFLOP/s fp64
