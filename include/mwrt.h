@@ -44,6 +44,8 @@ extern "C" {
 #define MWRT_ST_NEG_ABS 2    /* negative absorption met in the layer integration -> outputs NaN
                                 (PyRTlib's exponential_integration raises ValueError) */
 #define MWRT_ST_DUCTING 4    /* ray tracing hit a non-physical argument; remaining ds = 0 (PyRTlib warns) */
+#define MWRT_ST_RANGE 8      /* temperature outside (50 K, 1000 K) -> outputs NaN (the reference's realism
+                                window is 0..400 K, preprocessing4all.py:553-572) */
 
 /* flags of mwrt_plan_create */
 #define MWRT_F_RAY_TRACING 1 /* refractive slant path (TbCloudRTE(ray_tracing=True)); default 1/sin(elev) */

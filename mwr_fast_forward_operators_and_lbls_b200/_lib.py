@@ -5,13 +5,13 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmwrt.so")
+LIB_PATH = os.environ.get("MWRT_LIB") or os.path.join(HERE, "libmwrt.so")  # override: experiments only
 
 H2O_COLS = ("fl", "s1", "b2", "w0", "x", "w0s", "xs", "sr", "sh", "xh", "shs", "xhs", "aair", "aself",
             "w2", "w2s", "d2", "d2s")
 O2_COLS = ("f", "s300", "be", "w300", "y0", "y1", "g0", "g1", "dnu0", "dnu1")
 
-ST_NAN_INPUT, ST_NEG_ABS, ST_DUCTING = 1, 2, 4
+ST_NAN_INPUT, ST_NEG_ABS, ST_DUCTING, ST_RANGE = 1, 2, 4, 8
 F_RAY_TRACING, F_FROM_SAT, F_CLOUDY, F_TAU_LAYERS = 1, 2, 4, 8
 E_ARG, E_MODEL, E_NOMEM, E_STATE = -1, -2, -3, -4
 

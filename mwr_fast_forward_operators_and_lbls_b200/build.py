@@ -11,7 +11,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libmwrt.so")
+LIB = os.environ.get("MWRT_LIB_OUT") or os.path.join(HERE, "libmwrt.so")  # override: experiments only
 SOURCES = ["mwrt_api.cu", "mwrt_absorption.cu", "mwrt_rte.cu", "mwrt_peak.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--fmad=true"]
@@ -42,7 +42,8 @@ def build(force=False, verbose=False):
     log = []
     for src in SOURCES:
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = ([nvcc] + NVCC_FLAGS + os.environ.get("MWRT_NVCC_EXTRA", "").split()
+               + ["-c", os.path.join(CSRC, src), "-o", obj])
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode != 0:

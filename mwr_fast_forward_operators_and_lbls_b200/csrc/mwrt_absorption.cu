@@ -25,8 +25,73 @@ namespace mwrt {
 
 constexpr int kAbsThreads = 128;
 
+// rare-path helpers are kept out of line: the hot loops must stay small enough for the
+// instruction caches (the first version inlined them 14x and stalled on instruction fetch)
+__device__ __noinline__ double sd_shape_re(double width0, double width2, double delta2, double df) {
+  return sd_shape(width0, width2, delta2, df).re;
+}
+__device__ __noinline__ double o2_sd118_sf1(double df, double d1, double y) {
+  const double width2 = 0.076 * df;
+  cplx xc = cmake((df - 1.5 * width2) / width2, d1 / width2);
+  cplx xrt = csqrt_(xc);
+  cplx pxw = cscale(cmul(xrt, dcerror(-xrt.im, xrt.re)), kSqrtPi);
+  cplx one_m = cmake(2.0 * (1.0 - pxw.re), -2.0 * pxw.im);
+  cplx asd = cmul(cmake(1.0, y), one_m);
+  return asd.re / width2;
+}
+// Rayleigh liquid-water absorption per unit density [Np km^-1 / (g m^-3)]
+__device__ __noinline__ double liq_abs_unit(int liq_model, double f, double tk) {
+  cplx eps;
+  if (liq_model == 0) {  // Liebe-91 double Debye
+    const double theta1 = 1.0 - 300.0 / tk;
+    const double eps0 = 77.66 - 103.3 * theta1;
+    const double eps1 = 0.0671 * eps0;
+    const double eps2 = 3.52;
+    const double fp = (316.0 * theta1 + 146.4) * theta1 + 20.2;
+    const double fs = 39.8 * fp;
+    eps = cadd(cdiv(cmake(eps0 - eps1, 0.0), cmake(1.0, f / fp)),
+               cdiv(cmake(eps1 - eps2, 0.0), cmake(1.0, f / fs)));
+    eps.re += eps2;
+  } else {  // Rosenkranz (2015) `dilec12`
+    const double tc = tk - 273.15;
+    const double theta = 300.0 / tk;
+    const double lnth = log(theta);
+    const double kap0 = -43.7527 * exp(0.05 * lnth) + 299.504 * exp(1.47 * lnth) -
+                        399.364 * exp(2.11 * lnth) + 221.327 * exp(2.31 * lnth);
+    const double delta = 80.69715 * exp(-tc / 226.45);
+    const double sd = 1164.023 * exp(-651.4728 / (tc + 133.07));
+    const double deltb = 4.008724 * exp(-tc / 103.05);
+    const double hdelta = deltb / 2.0;
+    const double f1 = 10.46012 + 0.1454962 * tc + 0.063267156 * (tc * tc) +
+                      0.00093786645 * (tc * tc * tc);
+    const cplx z1 = cmake(-0.75 * f1, f1);
+    const cplx z2 = cmake(-4500.0, 2000.0);
+    const cplx cnorm = clog_(cdiv(z2, z1));
+    const cplx z = cmake(0.0, f);
+    cplx kappa = cmake(kap0, 0.0);
+    kappa = csub(kappa, cdiv(cscale(z, delta), cmake(sd, f)));
+    cplx chip = cdiv(cscale(clog_(cdiv(csub(z, z2), csub(z, z1))), hdelta), cnorm);
+    cplx chij = cdiv(cscale(clog_(cdiv(csub(z, cconj(z2)), csub(z, cconj(z1)))), hdelta),
+                     cconj(cnorm));
+    eps = cadd(kappa, cmake(chip.re + chij.re - deltb, chip.im + chij.im));
+  }
+  cplx re = cdiv(cmake(eps.re - 1.0, eps.im), cmake(eps.re + 2.0, eps.im));
+  return -0.06286 * re.im * f;
+}
+
+// frequency-independent state of one H2O / O2 line at one level-point
+struct H2OLine {
+  double w, wsq, base, shift, sp, w2, dl2;
+};
+struct O2Line {
+  double fcen, df, df2, as, ys, sp, y, gfac;
+};
+
+#ifndef MWRT_ABS_MINB
+#define MWRT_ABS_MINB 4
+#endif
 template <int FB>
-__global__ void __launch_bounds__(kAbsThreads)
+__global__ void __launch_bounds__(kAbsThreads, MWRT_ABS_MINB)
 k_absorption(const ModelDev m, const long long npts, const int L, const int F,
              const double* __restrict__ p_in, const double* __restrict__ tk_in,
              const double* __restrict__ e_in, const int e_is_rh, double* __restrict__ e_out,
@@ -40,6 +105,8 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
   double* fblk = tab + m.n_table;         // FB frequencies of this block
   double* dfm = fblk + FB;                // nh x FB: f_j - fl_i
   double* dfp = dfm + nh * FB;            // nh x FB: f_j + fl_i
+  double* ifl2 = dfp + nh * FB;           // nh: 1/fl_i^2
+  double* ifk2 = ifl2 + nh;               // no: 1/f_k^2
   const int f0 = blockIdx.y * FB;
   for (int i = threadIdx.x; i < m.n_table; i += blockDim.x) tab[i] = m.tables[i];
   if (threadIdx.x < FB) {
@@ -52,6 +119,15 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     dfm[i] = f - fl;
     dfp[i] = f + fl;
   }
+  for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+    double fl = tab[MWRT_H2O_FL * nh + i];
+    ifl2[i] = 1.0 / (fl * fl);
+  }
+  const double* O = tab + MWRT_H2O_NCOL * nh;
+  for (int i = threadIdx.x; i < no; i += blockDim.x) {
+    double fk = O[MWRT_O2_F * no + i];
+    ifk2[i] = 1.0 / (fk * fk);
+  }
   __syncthreads();
 
   const long long ipt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,14 +136,20 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
   const int lev = (int)(ipt - pidx * L);
 
   const double p_mb = p_in[ipt];
-  const double tk = tk_in[ipt];
+  const double tk_raw = tk_in[ipt];
+  // the branch-free exp needs bounded arguments: temperatures outside (50 K, 1000 K) are computed
+  // with a stand-in and reported as NaN + status (the reference's realism window is 0..400 K)
+  const bool t_ok = (tk_raw > 50.0) && (tk_raw < 1000.0);
+  const double tk = t_ok ? tk_raw : 300.0;
   double e_mb = e_in[ipt];
   const bool first = (blockIdx.y == 0);
   if (e_is_rh) e_mb = e_mb * goff_gratch_es(tk);
+  const bool in_nan = isnan(p_mb) || isnan(tk_raw) || isnan(e_mb);
+  const bool in_bad = in_nan || !t_ok;
   if (first) {
-    if (e_out) e_out[ipt] = e_mb;
-    if (rho_out) rho_out[ipt] = e_mb / ((kRWatVap * 1e-05) * tk);
-    if (status && (isnan(p_mb) || isnan(tk) || isnan(e_mb))) atomicOr(&status[pidx], MWRT_ST_NAN_INPUT);
+    if (e_out) e_out[ipt] = in_bad ? nan("") : e_mb;
+    if (rho_out) rho_out[ipt] = in_bad ? nan("") : e_mb / ((kRWatVap * 1e-05) * tk);
+    if (status && in_bad) atomicOr(&status[pidx], in_nan ? MWRT_ST_NAN_INPUT : MWRT_ST_RANGE);
   }
 
   double fmin = fblk[0], fmax = fblk[0];
@@ -87,6 +169,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
 
   const long long obase = (pidx * F + f0) * (long long)L + lev;  // + j*L per frequency
   double acc[FB];
+  double tmp[FB];  // rare-path scratch (local memory, dynamically indexed)
 
   // ------------------------------------------------------------------ H2O (abh2o)
   {
@@ -96,67 +179,73 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     const double tic = m.h2o_reftcon / t;
     const double ticln = log(tic);
     const double conbase =
-        (m.h2o_cf * pda * exp(m.h2o_xcf * ticln) + m.h2o_cs * pvap * exp(m.h2o_xcs * ticln)) * pvap;
+        (m.h2o_cf * pda * exp_nb(m.h2o_xcf * ticln) + m.h2o_cs * pvap * exp_nb(m.h2o_xcs * ticln)) * pvap;
     const double ti = m.h2o_reftline / t;
     const double tiln = log(ti);
+    const double omti = 1.0 - ti;
     const double* H = tab;
+    const bool sd_on = m.h2o_sd != 0;
+
+    auto hoist = [&](int i) {
+      H2OLine h;
+      h.w = H[MWRT_H2O_W0 * nh + i] * pda * exp_nb(H[MWRT_H2O_X * nh + i] * tiln) +
+            H[MWRT_H2O_W0S * nh + i] * pvap * exp_nb(H[MWRT_H2O_XS * nh + i] * tiln);
+      const double shf = H[MWRT_H2O_SH * nh + i] * pda * (1.0 - H[MWRT_H2O_AAIR * nh + i] * tiln) *
+                         exp_nb(H[MWRT_H2O_XH * nh + i] * tiln);
+      const double shs = H[MWRT_H2O_SHS * nh + i] * pvap * (1.0 - H[MWRT_H2O_ASELF * nh + i] * tiln) *
+                         exp_nb(H[MWRT_H2O_XHS * nh + i] * tiln);
+      h.shift = H[MWRT_H2O_SR * nh + i] * h.w + shf + shs;
+      h.w2 = sd_on ? H[MWRT_H2O_W2 * nh + i] * pda + H[MWRT_H2O_W2S * nh + i] * pvap : 0.0;
+      h.dl2 = sd_on ? H[MWRT_H2O_D2 * nh + i] * pda + H[MWRT_H2O_D2S * nh + i] * pvap : 0.0;
+      h.wsq = h.w * h.w;
+      h.base = h.w * rcp_fast(562500.0 + h.wsq);
+      // strength with (1/fl)^2 folded in; the common f^2 is applied once at the end
+      h.sp = H[MWRT_H2O_S1 * nh + i] * exp_nb(fma(2.5, tiln, H[MWRT_H2O_B2 * nh + i] * omti)) * ifl2[i];
+      return h;
+    };
+
 #pragma unroll
     for (int j = 0; j < FB; ++j) acc[j] = 0.0;
     double basesum = 0.0;
+    H2OLine nxt = hoist(0);
     for (int i = 0; i < nh; ++i) {
-      const double fl = H[MWRT_H2O_FL * nh + i];
-      const double w = H[MWRT_H2O_W0 * nh + i] * pda * exp(H[MWRT_H2O_X * nh + i] * tiln) +
-                       H[MWRT_H2O_W0S * nh + i] * pvap * exp(H[MWRT_H2O_XS * nh + i] * tiln);
-      double shf = H[MWRT_H2O_SH * nh + i] * pda * (1.0 - H[MWRT_H2O_AAIR * nh + i] * tiln);
-      const double xh = H[MWRT_H2O_XH * nh + i];
-      if (xh != 0.0) shf *= exp(xh * tiln);
-      double shs = H[MWRT_H2O_SHS * nh + i] * pvap * (1.0 - H[MWRT_H2O_ASELF * nh + i] * tiln);
-      const double xhs = H[MWRT_H2O_XHS * nh + i];
-      if (xhs != 0.0) shs *= exp(xhs * tiln);
-      const double shift = H[MWRT_H2O_SR * nh + i] * w + shf + shs;
-      double w2 = 0.0, dl2 = 0.0;
-      if (m.h2o_sd) {
-        w2 = H[MWRT_H2O_W2 * nh + i] * pda + H[MWRT_H2O_W2S * nh + i] * pvap;
-        dl2 = H[MWRT_H2O_D2 * nh + i] * pda + H[MWRT_H2O_D2S * nh + i] * pvap;
-      }
-      const double wsq = w * w;
-      const double base = w / (562500.0 + wsq);
-      // strength with (1/fl)^2 folded in; the common f^2 is applied once at the end
-      const double sp = H[MWRT_H2O_S1 * nh + i] *
-                        exp(2.5 * tiln + H[MWRT_H2O_B2 * nh + i] * (1.0 - ti)) / (fl * fl);
-      const double fc = fl + shift;
+      const H2OLine h = nxt;
+      nxt = hoist(i + 1 < nh ? i + 1 : i);  // next line's exp chains overlap this line's wing loop
       const double* dm = dfm + i * FB;
       const double* dp = dfp + i * FB;
-      const bool all_in = !(w2 > 0.0) && (fc + fmax < 750.0) && (fc - fmin < 750.0) &&
-                          (fmax - fc < 750.0);
-      if (all_in) {
-        // both wings inside the 750 GHz cutoff for every frequency of the block:
-        //   w/(d0^2+w^2) + w/(d1^2+w^2) = w (D0+D1) / (D0 D1)   -> one reciprocal per (line, f)
-        const double sw = sp * w;
-        basesum = fma(2.0 * sp, base, basesum);
+      // unconditional fast form, both wings inside the 750 GHz cutoff, plain Lorentz:
+      //   w/(d0^2+w^2) + w/(d1^2+w^2) = w (D0+D1) / (D0 D1)   -> one reciprocal per (line, f)
+      const double sw = h.sp * h.w;
+      basesum = fma(2.0 * h.sp, h.base, basesum);
 #pragma unroll
+      for (int j = 0; j < FB; ++j) {
+        const double d0 = dm[j] - h.shift;
+        const double d1 = dp[j] + h.shift;
+        const double D0 = fma(d0, d0, h.wsq);
+        const double D1 = fma(d1, d1, h.wsq);
+        const double q = (D0 + D1) * rcp_fast(D0 * D1);
+        acc[j] = fma(sw, q, acc[j]);
+      }
+      // rare corrections: a wing beyond the cutoff, or the speed-dependent shape near line centre
+      const double fc = tab[MWRT_H2O_FL * nh + i] + h.shift;
+      const bool all_in = (fc + fmax < 750.0) && (fc - fmin < 750.0) && (fmax - fc < 750.0);
+      const bool sd_any = (h.w2 > 0.0) && (fmin - fc < 10.0 * h.w) && (fc - fmax < 10.0 * h.w);
+      if (!all_in || sd_any) {
+#pragma unroll 1
         for (int j = 0; j < FB; ++j) {
-          const double d0 = dm[j] - shift;
-          const double d1 = dp[j] + shift;
-          const double D0 = fma(d0, d0, wsq);
-          const double D1 = fma(d1, d1, wsq);
-          const double q = (D0 + D1) * rcp_fast(D0 * D1);
-          acc[j] = fma(sw, q, acc[j]);
+          const double d0 = dm[j] - h.shift;
+          const double d1 = dp[j] + h.shift;
+          const double l0 = div_fast(h.w, fma(d0, d0, h.wsq));
+          double c = 0.0;
+          if (h.w2 > 0.0 && fabs(d0) < 10.0 * h.w)
+            c += sd_shape_re(h.w, h.w2, h.dl2, d0) - l0;   // replace Lorentz by the SD shape
+          else if (!(fabs(d0) < 750.0))
+            c -= l0 - h.base;                               // wing outside the cutoff: remove it
+          if (!(fabs(d1) < 750.0)) c -= div_fast(h.w, fma(d1, d1, h.wsq)) - h.base;
+          tmp[j] = c;
         }
-      } else {
 #pragma unroll
-        for (int j = 0; j < FB; ++j) {
-          const double d0 = dm[j] - shift;
-          const double d1 = dp[j] + shift;
-          double r = 0.0;
-          if (w2 > 0.0 && fabs(d0) < 10.0 * w) {
-            r += sd_shape(w, w2, dl2, d0).re - base;
-          } else if (fabs(d0) < 750.0) {
-            r += div_fast(w, fma(d0, d0, wsq)) - base;
-          }
-          if (fabs(d1) < 750.0) r += div_fast(w, fma(d1, d1, wsq)) - base;
-          acc[j] = fma(sp, r, acc[j]);
-        }
+        for (int j = 0; j < FB; ++j) acc[j] = fma(h.sp, tmp[j], acc[j]);
       }
     }
     const double lc = m.h2o_line_const * den;
@@ -165,6 +254,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
       const double f = fblk[j];
       double a = (f * f) * fma(lc, acc[j] - basesum, conbase);
       if (rho <= 0.0) a = 0.0;
+      if (in_bad) a = nan("");
       if (f0 + j < F) awet[obase + (long long)j * L] = a;
     }
   }
@@ -174,151 +264,106 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     const double th = 300.0 / t;
     const double th1 = th - 1.0;
     const double thln = log(th);
-    const double b = exp(m.o2_x * thln);
+    const double b = exp_nb(m.o2_x * thln);
     const double preswv = rho * t / m.o2_pvap_div;
     const double presda = pp - preswv;
     const double den = 0.001 * (presda * b + m.o2_h2o_broad * preswv * th);
     const double dens = 0.001 * (presda + m.o2_h2o_broad * preswv) * th;
     const double dfnr = m.o2_wb300 * den;
-    const double pe2 = den * den;
+    const double pe2 = (m.o2_mixing == 1) ? 0.0 : den * den;   // first order: g = 1, no line shift
     const double ymul = (m.o2_mixing == 1) ? 0.001 * pp * b : den;
-    const double* O = tab + MWRT_H2O_NCOL * nh;
+    const bool dens118 = m.o2_dens118 != 0;
+
+    auto hoist = [&](int k) {
+      O2Line o;
+      const double wden = (dens118 && k == 0) ? dens : den;
+      o.df = O[MWRT_O2_W300 * no + k] * wden;
+      o.y = ymul * (O[MWRT_O2_Y0 * no + k] + O[MWRT_O2_Y1 * no + k] * th1);
+      o.gfac = 1.0 + pe2 * (O[MWRT_O2_G0 * no + k] + O[MWRT_O2_G1 * no + k] * th1);
+      o.fcen = O[MWRT_O2_F * no + k] + pe2 * (O[MWRT_O2_DNU0 * no + k] + O[MWRT_O2_DNU1 * no + k] * th1);
+      o.sp = O[MWRT_O2_S300 * no + k] * exp_nb(-O[MWRT_O2_BE * no + k] * th1) * ifk2[k];
+      o.df2 = o.df * o.df;
+      o.as = o.sp * (o.df * o.gfac);
+      o.ys = o.sp * o.y;
+      return o;
+    };
+
 #pragma unroll
     for (int j = 0; j < FB; ++j) acc[j] = 0.0;
+    O2Line nxt = hoist(0);
     for (int k = 0; k < no; ++k) {
-      const double fk = O[MWRT_O2_F * no + k];
-      double df = O[MWRT_O2_W300 * no + k] * den;
-      if (m.o2_dens118 && k == 0) df = O[MWRT_O2_W300 * no] * dens;
-      const double y = ymul * (O[MWRT_O2_Y0 * no + k] + O[MWRT_O2_Y1 * no + k] * th1);
-      double gfac = 1.0, fcen = fk;
-      if (m.o2_mixing != 1) {
-        gfac = 1.0 + pe2 * (O[MWRT_O2_G0 * no + k] + O[MWRT_O2_G1 * no + k] * th1);
-        fcen = fk + pe2 * (O[MWRT_O2_DNU0 * no + k] + O[MWRT_O2_DNU1 * no + k] * th1);
+      const O2Line o = nxt;
+      nxt = hoist(k + 1 < no ? k + 1 : k);
+      // sf1 + sf2 = (n1 D2 + n2 D1) / (D1 D2), strength folded into the numerators
+#pragma unroll
+      for (int j = 0; j < FB; ++j) {
+        const double f = fblk[j];
+        const double d1 = f - o.fcen;
+        const double d2 = f + o.fcen;
+        const double D1 = fma(d1, d1, o.df2);
+        const double D2 = fma(d2, d2, o.df2);
+        const double n1 = fma(d1, o.ys, o.as);
+        const double n2 = fma(-d2, o.ys, o.as);
+        const double num = fma(n1, D2, n2 * D1);
+        acc[j] = fma(num, rcp_fast(D1 * D2), acc[j]);
       }
-      const double sp = O[MWRT_O2_S300 * no + k] * exp(-O[MWRT_O2_BE * no + k] * th1) / (fk * fk);
-      const double df2 = df * df;
-      if (m.o2_sd118 && k == 0) {
-#pragma unroll
+      if (m.o2_sd118 && k == 0 && (fmin - o.fcen < 10.0 * o.df) && (o.fcen - fmax < 10.0 * o.df)) {
+        // speed-dependent 118.75 GHz line: replace sf1 where |f - fcen| < 10 df
+#pragma unroll 1
         for (int j = 0; j < FB; ++j) {
-          const double f = fblk[j];
-          const double d1 = f - fcen, d2 = f + fcen;
-          double sf1;
-          if (fabs(d1) < 10.0 * df) {
-            const double width2 = 0.076 * df;
-            cplx xc = cmake((df - 1.5 * width2) / width2, d1 / width2);
-            cplx xrt = csqrt_(xc);
-            cplx pxw = cscale(cmul(xrt, dcerror(-xrt.im, xrt.re)), kSqrtPi);
-            cplx one_m = cmake(2.0 * (1.0 - pxw.re), -2.0 * pxw.im);
-            cplx asd = cmul(cmake(1.0, y), one_m);
-            sf1 = asd.re / width2;
-          } else {
-            sf1 = div_fast(df * gfac + d1 * y, fma(d1, d1, df2));
-          }
-          const double sf2 = div_fast(df * gfac - d2 * y, fma(d2, d2, df2));
-          acc[j] = fma(sp, sf1 + sf2, acc[j]);
+          const double d1 = fblk[j] - o.fcen;
+          double c = 0.0;
+          if (fabs(d1) < 10.0 * o.df)
+            c = o2_sd118_sf1(o.df, d1, o.y) - div_fast(o.df * o.gfac + d1 * o.y, fma(d1, d1, o.df2));
+          tmp[j] = c;
         }
-      } else {
-        // sf1 + sf2 = (n1 D2 + n2 D1) / (D1 D2), strength folded into the numerators
-        const double as = sp * (df * gfac);
-        const double ys = sp * y;
 #pragma unroll
-        for (int j = 0; j < FB; ++j) {
-          const double f = fblk[j];
-          const double d1 = f - fcen;
-          const double d2 = f + fcen;
-          const double D1 = fma(d1, d1, df2);
-          const double D2 = fma(d2, d2, df2);
-          const double n1 = fma(d1, ys, as);
-          const double n2 = fma(-d2, ys, as);
-          const double num = fma(n1, D2, n2 * D1);
-          acc[j] = fma(num, rcp_fast(D1 * D2), acc[j]);
-        }
+        for (int j = 0; j < FB; ++j) acc[j] = fma(o.sp, tmp[j], acc[j]);
       }
     }
     const double scale = m.o2_abs_const * presda * (th * th * th);
     const double pdry_mb = pdrykpa * 10.0;
-    const double n2base = m.n2_n * (m.n2_l * pdry_mb * pdry_mb * exp(m.n2_m * thln));
+    const double n2base = m.n2_n * (m.n2_l * pdry_mb * pdry_mb * exp_nb(m.n2_m * thln));
 #pragma unroll
     for (int j = 0; j < FB; ++j) {
       const double f = fblk[j];
       const double f2 = f * f;
-      const double nonres = m.o2_nonres * dfnr / (th * (f2 + dfnr * dfnr));
+      const double nonres = m.o2_nonres * dfnr * rcp_fast(th * fma(dfnr, dfnr, f2));
       double o2 = scale * (f2 * (nonres + acc[j]));
-      o2 = (o2 < 0.0) ? 0.0 : o2;  // max(o2abs, 0) that keeps NaN (fmax would drop it)
+      o2 = (o2 < 0.0) ? 0.0 : o2;  // max(o2abs, 0)
       o2 *= m.o2_iso;
       double fdep = 1.0;
       if (m.n2_fdep) {
-        const double fr = f / 450.0;
-        fdep = 0.5 + 0.5 / (1.0 + fr * fr);
+        const double fr = f * (1.0 / 450.0);
+        fdep = 0.5 + 0.5 * rcp_fast(fma(fr, fr, 1.0));
       }
-      const double an2 = n2base * fdep * f2;
-      if (f0 + j < F) adry[obase + (long long)j * L] = o2 + an2;
+      double a = o2 + n2base * fdep * f2;
+      if (in_bad) a = nan("");
+      if (f0 + j < F) adry[obase + (long long)j * L] = a;
     }
   }
 
   // ------------------------------------------------------------------ cloud
   if (aliq) {
     const double denl = denliq ? denliq[ipt] : 0.0;
-    if (denl > 0.0 || isnan(denl)) {
-      if (m.liq_model == 0) {  // Liebe-91 double Debye
-        const double theta1 = 1.0 - 300.0 / tk;
-        const double eps0 = 77.66 - 103.3 * theta1;
-        const double eps1 = 0.0671 * eps0;
-        const double eps2 = 3.52;
-        const double fp = (316.0 * theta1 + 146.4) * theta1 + 20.2;
-        const double fs = 39.8 * fp;
-#pragma unroll
-        for (int j = 0; j < FB; ++j) {
-          const double f = fblk[j];
-          cplx eps = cadd(cdiv(cmake(eps0 - eps1, 0.0), cmake(1.0, f / fp)),
-                          cdiv(cmake(eps1 - eps2, 0.0), cmake(1.0, f / fs)));
-          eps.re += eps2;
-          cplx re = cdiv(cmake(eps.re - 1.0, eps.im), cmake(eps.re + 2.0, eps.im));
-          if (f0 + j < F) aliq[obase + (long long)j * L] = -0.06286 * re.im * f * denl;
-        }
-      } else {  // Rosenkranz (2015) `dilec12`
-        const double tc = tk - 273.15;
-        const double theta = 300.0 / tk;
-        const double lnth = log(theta);
-        const double kap0 = -43.7527 * exp(0.05 * lnth) + 299.504 * exp(1.47 * lnth) -
-                            399.364 * exp(2.11 * lnth) + 221.327 * exp(2.31 * lnth);
-        const double delta = 80.69715 * exp(-tc / 226.45);
-        const double sd = 1164.023 * exp(-651.4728 / (tc + 133.07));
-        const double deltb = 4.008724 * exp(-tc / 103.05);
-        const double hdelta = deltb / 2.0;
-        const double f1 = 10.46012 + 0.1454962 * tc + 0.063267156 * (tc * tc) +
-                          0.00093786645 * (tc * tc * tc);
-        const cplx z1 = cmake(-0.75 * f1, f1);
-        const cplx z2 = cmake(-4500.0, 2000.0);
-        const cplx cnorm = clog_(cdiv(z2, z1));
+    const bool wet = denl > 0.0 || isnan(denl);
 #pragma unroll 1
-        for (int j = 0; j < FB; ++j) {
-          const double f = fblk[j];
-          const cplx z = cmake(0.0, f);
-          cplx kappa = cmake(kap0, 0.0);
-          kappa = csub(kappa, cdiv(cscale(z, delta), cmake(sd, f)));
-          cplx chip = cdiv(cscale(clog_(cdiv(csub(z, z2), csub(z, z1))), hdelta), cnorm);
-          cplx chij = cdiv(cscale(clog_(cdiv(csub(z, cconj(z2)), csub(z, cconj(z1)))), hdelta),
-                           cconj(cnorm));
-          cplx eps = cadd(kappa, cmake(chip.re + chij.re - deltb, chip.im + chij.im));
-          cplx re = cdiv(cmake(eps.re - 1.0, eps.im), cmake(eps.re + 2.0, eps.im));
-          if (f0 + j < F) aliq[obase + (long long)j * L] = -0.06286 * re.im * f * denl;
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < FB; ++j)
-        if (f0 + j < F) aliq[obase + (long long)j * L] = 0.0;
+    for (int j = 0; j < FB; ++j) {
+      double a = 0.0;
+      if (wet) a = liq_abs_unit(m.liq_model, fblk[j], tk) * denl;
+      if (in_bad) a = nan("");
+      if (f0 + j < F) aliq[obase + (long long)j * L] = a;
     }
   }
   if (aice) {
     const double deni = denice ? denice[ipt] : 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < FB; ++j) {
       const double f = fblk[j];
       const double wave = kLightC / (f * 1e9);
       double a = 0.0;
       if (deni > 0.0 || isnan(deni)) a = ((8.18645 / wave) * deni * 0.000959553) * kDb2Np;
+      if (in_bad) a = nan("");
       if (f0 + j < F) aice[obase + (long long)j * L] = a;
     }
   }
@@ -331,7 +376,7 @@ static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, c
                       double* adry, double* aliq, double* aice, int* status, cudaStream_t st) {
   const long long npts = (long long)P * L;
   dim3 grid((unsigned)((npts + kAbsThreads - 1) / kAbsThreads), (unsigned)((F + FB - 1) / FB));
-  size_t smem = sizeof(double) * (size_t)(m.n_table + FB + 2 * m.n_h2o * FB);
+  size_t smem = sizeof(double) * (size_t)(m.n_table + FB + 2 * m.n_h2o * FB + m.n_h2o + m.n_o2);
   k_absorption<FB><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, p, tk, e, e_is_rh, e_out, rho_out,
                                                     denliq, denice, frq, awet, adry, aliq, aice,
                                                     status);

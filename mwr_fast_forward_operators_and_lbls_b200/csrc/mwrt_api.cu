@@ -3,6 +3,7 @@
 //
 // Boundary it replaces: TbCloudRTE(z,p,t,rh,frq,ang) / init_absmdl / satellite / execute() as called at
 // /root/reference/python_src/proc/PyRTlib_processing.py:123-127 -- see INTEGRATION.md.
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -31,10 +32,10 @@ int absorption_launch(const ModelDev& m, int P, int L, int F, const double* p, c
                       double* adry, double* aliq, double* aice, int* status, cudaStream_t st);
 int vapor_launch(long long n, const double* tk, const double* rh, double* e, double* rho, cudaStream_t st);
 int rte_launch(int P, int L, int F, int A, const double* tk, const double* awet, const double* adry,
-               const double* aliq, const double* aice, const double* ds, const double* frq,
-               int from_sat, double emis, double* tbtotal, double* tbatm, double* tmr,
-               double* tauwet, double* taudry, double* tauliq, double* tauice, double* tau_layer,
-               int tl_angle, int* status, cudaStream_t st);
+               const double* aliq, const double* aice, const double* ds, const double* z,
+               const double* amass, const double* frq, int from_sat, double emis, double* tbtotal,
+               double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
+               double* tauice, double* tau_layer, int tl_angle, int* status, cudaStream_t st);
 int slant_path_launch(int P, int L, int A, const double* z, const double* p, const double* tk,
                       const double* e, const double* angles, int ray_tracing, double* ds, int* status,
                       cudaStream_t st);
@@ -64,6 +65,7 @@ struct mwrt_plan {
   int C, S;          // band-pass (C == 0: off)
   double* d_frq;
   double* d_angles;
+  double* d_amass;   // (A,) 1/sin(elevation), computed on the host like PyRTlib does
   double* d_bpw;     // (C,S) weights or null (uniform)
   // workspace for `cap` profiles
   int cap;
@@ -198,7 +200,7 @@ int mwrt_rte_f64(int P, int L, int F, int A, const double* tk, const double* awe
     return fail_arg(MWRT_E_ARG, "mwrt_rte_f64: aliq and aice must be given together");
   if (tau_layer && (tau_layer_angle < 0 || tau_layer_angle >= A))
     return fail_arg(MWRT_E_ARG, "mwrt_rte_f64: tau_layer_angle out of range");
-  return rte_launch(P, L, F, A, tk, awet, adry, aliq, aice, ds, frq, from_sat, emissivity, tbtotal,
+  return rte_launch(P, L, F, A, tk, awet, adry, aliq, aice, ds, nullptr, nullptr, frq, from_sat, emissivity, tbtotal,
                     tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tau_layer_angle, status,
                     (cudaStream_t)stream);
 }
@@ -263,8 +265,12 @@ int mwrt_plan_create(const mwrt_model* m, int L, int F, int A, const double* frq
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_angles, sizeof(double) * A);
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_frq, frq, sizeof(double) * F, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_angles, angles, sizeof(double) * A, cudaMemcpyHostToDevice);
+  std::vector<double> amass(A);
+  for (int a = 0; a < A; ++a) amass[a] = 1.0 / sin(angles[a] * 3.141592653589793 / 180.0);
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_amass, sizeof(double) * A);
+  if (e == cudaSuccess) e = cudaMemcpy(pl->d_amass, amass.data(), sizeof(double) * A, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
-    cudaFree(pl->d_frq); cudaFree(pl->d_angles);
+    cudaFree(pl->d_frq); cudaFree(pl->d_angles); cudaFree(pl->d_amass);
     delete pl;
     return fail_cuda(e, "mwrt_plan_create");
   }
@@ -290,7 +296,7 @@ int mwrt_plan_destroy(mwrt_plan* pl) {
   if (!pl) return 0;
   plan_free_host(pl);
   plan_free_ws(pl);
-  cudaFree(pl->d_frq); cudaFree(pl->d_angles); cudaFree(pl->d_bpw);
+  cudaFree(pl->d_frq); cudaFree(pl->d_angles); cudaFree(pl->d_amass); cudaFree(pl->d_bpw);
   delete pl;
   return 0;
 }
@@ -320,7 +326,7 @@ int mwrt_plan_set_bandpass(mwrt_plan* pl, int C, int S, const double* weights) {
 int mwrt_plan_launch_count(const mwrt_plan* pl, int P) {
   if (!pl || P <= 0) return 0;
   const int nchunk = (P + pl->chunk - 1) / pl->chunk;
-  return nchunk * (3 + (pl->C > 0 ? 7 : 0));
+  return nchunk * (2 + ((pl->flags & MWRT_F_RAY_TRACING) ? 1 : 0) + (pl->C > 0 ? 7 : 0));
 }
 
 // one chunk: device pointers already offset to the chunk's first profile
@@ -336,17 +342,19 @@ static int forward_chunk(mwrt_plan* pl, int P, const mwrt_profiles& in, const mw
                              pl->w_awet, pl->w_adry, cloudy ? pl->w_aliq : nullptr,
                              cloudy ? pl->w_aice : nullptr, out.status, st);
   if (rc) return rc;
-  // kernel 2: slant path
-  rc = slant_path_launch(P, L, A, in.z, in.p, in.tk, pl->w_e, pl->d_angles, rt ? 1 : 0, pl->w_ds,
-                         out.status, st);
-  if (rc) return rc;
+  // kernel 2: refractive slant path (the plane-parallel default needs no kernel: kernel 3 forms
+  // ds = dz / sin(elev) in registers)
+  if (rt) {
+    rc = slant_path_launch(P, L, A, in.z, in.p, in.tk, pl->w_e, pl->d_angles, 1, pl->w_ds, out.status, st);
+    if (rc) return rc;
+  }
   // kernel 3: RTE (+ band-pass epilogue)
   double* tl = (pl->flags & MWRT_F_TAU_LAYERS) ? out.tau_layer : nullptr;
   double* dst[7] = {out.tbtotal, out.tbatm, out.tmr, out.tauwet, out.taudry, out.tauliq, out.tauice};
   double* mono[7];
   for (int i = 0; i < 7; ++i) mono[i] = (pl->C > 0) ? (dst[i] ? pl->w_mono[i] : nullptr) : dst[i];
   rc = rte_launch(P, L, F, A, in.tk, pl->w_awet, pl->w_adry, cloudy ? pl->w_aliq : nullptr,
-                  cloudy ? pl->w_aice : nullptr, pl->w_ds, pl->d_frq,
+                  cloudy ? pl->w_aice : nullptr, rt ? pl->w_ds : nullptr, in.z, pl->d_amass, pl->d_frq,
                   (pl->flags & MWRT_F_FROM_SAT) ? 1 : 0, pl->emis, mono[0], mono[1], mono[2], mono[3],
                   mono[4], mono[5], mono[6], tl, 0, out.status, st);
   if (rc) return rc;

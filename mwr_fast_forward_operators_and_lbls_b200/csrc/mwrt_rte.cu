@@ -17,8 +17,9 @@ namespace mwrt {
 
 constexpr int kRteThreads = 128;
 
-// One layer of exponential_integration without the ds factor.  Negative input -> NaN
-// (PyRTlib raises ValueError; the caller flags the profile with MWRT_ST_NEG_ABS).
+// One layer of exponential_integration without the ds factor: x0 = lower level,
+// x1 = upper level.  Negative input -> NaN (PyRTlib raises ValueError; the caller flags the profile
+// with MWRT_ST_NEG_ABS).
 __device__ __forceinline__ double layer_mean(double x0, double x1, bool zeroflg, bool& neg) {
   if (x0 < 0.0 || x1 < 0.0) {
     neg = true;
@@ -29,18 +30,24 @@ __device__ __forceinline__ double layer_mean(double x0, double x1, bool zeroflg,
   return (x1 - x0) / log(x1 / x0);
 }
 
+// modified Planck function 1/(exp(hvk/T) - 1); hvk/T is O(1e-2) for microwave frequencies
 __device__ __forceinline__ double planck_mod(double hvk, double t) { return 1.0 / (exp(hvk / t) - 1.0); }
 __device__ __forceinline__ double bright(double hvk, double b) {
   if (b > 0.0 || isnan(b)) return hvk / log(1.0 + 1.0 / b);
   return 0.0;
 }
 
-template <int NA, bool CLOUDY>
-__global__ void __launch_bounds__(kRteThreads)
+// PLANE = plane-parallel path: ds(a, layer) = dz(layer) * amass(a) is formed in registers from z and
+// a per-angle air-mass table (no ds array, no slant-path kernel); otherwise ds is read from (P,A,L).
+// measured on B200 (profiles/r01b_*): the plane-parallel variant is fastest capped at 128 registers
+// (4 CTAs/SM); the general variant spills there and runs best uncapped
+template <int NA, bool CLOUDY, bool PLANE>
+__global__ void __launch_bounds__(kRteThreads, (PLANE && !CLOUDY) ? 4 : 1)
 k_rte(const int P, const int L, const int F, const int A, const double* __restrict__ tk,
       const double* __restrict__ awet, const double* __restrict__ adry,
       const double* __restrict__ aliq, const double* __restrict__ aice,
-      const double* __restrict__ ds, const double* __restrict__ frq, const int from_sat,
+      const double* __restrict__ ds, const double* __restrict__ z,
+      const double* __restrict__ amass_tab, const double* __restrict__ frq, const int from_sat,
       const double emis, double* __restrict__ tbtotal, double* __restrict__ tbatm,
       double* __restrict__ tmr, double* __restrict__ tauwet, double* __restrict__ taudry,
       double* __restrict__ tauliq, double* __restrict__ tauice, double* __restrict__ tau_layer,
@@ -52,67 +59,111 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
   const int a0 = blockIdx.y * NA;
   const long long row = idx * (long long)L;  // (p*F + jf)*L
   const double* tkp = tk + p * L;
-  const double* dsp = ds + (p * A + a0) * (long long)L;
+  const double* zp = PLANE ? z + p * L : nullptr;
+  const double* dsp = PLANE ? nullptr : ds + (p * A + a0) * (long long)L;
   const double hvk = (frq[jf] * 1e9) * kPlanckH / kBoltzmannK;
 
-  double tauprof[NA], batm[NA], trans[NA], sw[NA], sd[NA], sl[NA], si[NA];
+  double batm[NA], trans[NA], amass[NA];
+  // species sums: per angle in the general case, one zenith-path sum (scaled at the end) if PLANE
+  constexpr int NS = PLANE ? 1 : NA;
+  double sw[NS], sd[NS], sl[NS], si[NS], tauprof[NS];
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
-    tauprof[a] = 0.0; batm[a] = 0.0; trans[a] = 1.0;
-    sw[a] = 0.0; sd[a] = 0.0; sl[a] = 0.0; si[a] = 0.0;
+    batm[a] = 0.0;
+    trans[a] = 1.0;
+    amass[a] = (PLANE && a0 + a < A) ? amass_tab[a0 + a] : 0.0;
   }
-  bool neg = false;
-  const int near0 = from_sat ? L - 1 : 0;
-  double bnear = planck_mod(hvk, tkp[near0]);
+#pragma unroll
+  for (int a = 0; a < NS; ++a) { sw[a] = 0.0; sd[a] = 0.0; sl[a] = 0.0; si[a] = 0.0; tauprof[a] = 0.0; }
+
+  bool neg = false, anynan = false;
   const bool want_tl = (tau_layer != nullptr) && (tl_angle >= a0) && (tl_angle < a0 + NA);
   if (want_tl) tau_layer[row] = 0.0;
+  const int dir = from_sat ? -1 : 1;
+  int lev = from_sat ? L - 1 : 0;       // level sequence starts at the observer's end
 
-  for (int step = 0; step < L - 1; ++step) {
-    const int j = from_sat ? (L - 1 - step) : (step + 1);  // layer j spans levels j-1 .. j
-    const int far = from_sat ? j - 1 : j;
-    const double xw = layer_mean(awet[row + j - 1], awet[row + j], true, neg);
-    const double xd = layer_mean(adry[row + j - 1], adry[row + j], true, neg);
+  // "prev" = level already passed (nearer to the observer); "cur" = next level, loaded one step ahead
+  double pw = awet[row + lev], pd = adry[row + lev];
+  double pl = 0.0, pi_ = 0.0;
+  if (CLOUDY) { pl = aliq[row + lev]; pi_ = aice[row + lev]; }
+  double pz = PLANE ? zp[lev] - zp[0] : 0.0;
+  double bnear = planck_mod(hvk, tkp[lev]);
+  int nlev = lev + dir;
+  double cw = awet[row + nlev], cd = adry[row + nlev], ct = tkp[nlev];
+  double cl = 0.0, ci = 0.0, cz = 0.0;
+  if (CLOUDY) { cl = aliq[row + nlev]; ci = aice[row + nlev]; }
+  if (PLANE) cz = zp[nlev] - zp[0];
+
+  for (int step = 1; step < L; ++step) {
+    const int clev = nlev;                       // level reached in this step
+    const int j = from_sat ? clev + 1 : clev;    // layer index (upper level of the layer)
+    const double xw1 = cw, xd1 = cd, xl1 = cl, xi1 = ci, t1 = ct, z1 = cz;
+    // prefetch the following level while this layer is integrated
+    nlev = clev + dir;
+    const int ld = (step + 1 < L) ? nlev : clev;
+    cw = awet[row + ld];
+    cd = adry[row + ld];
+    ct = tkp[ld];
+    if (CLOUDY) { cl = aliq[row + ld]; ci = aice[row + ld]; }
+    if (PLANE) cz = zp[ld] - zp[0];
+
+    // layer_mean(lower level, upper level): in downwelling order prev is the lower level
+    const double xw = from_sat ? layer_mean(xw1, pw, true, neg) : layer_mean(pw, xw1, true, neg);
+    const double xd = from_sat ? layer_mean(xd1, pd, true, neg) : layer_mean(pd, xd1, true, neg);
+    double xtot = xw + xd;
     double xl = 0.0, xi = 0.0;
     if (CLOUDY) {
-      xl = layer_mean(aliq[row + j - 1], aliq[row + j], false, neg);
-      xi = layer_mean(aice[row + j - 1], aice[row + j], false, neg);
+      xl = from_sat ? layer_mean(xl1, pl, false, neg) : layer_mean(pl, xl1, false, neg);
+      xi = from_sat ? layer_mean(xi1, pi_, false, neg) : layer_mean(pi_, xi1, false, neg);
+      xtot = xtot + xi + xl;
     }
-    const double bfar = planck_mod(hvk, tkp[far]);
+    anynan |= isnan(xtot);
+    const double bfar = planck_mod(hvk, t1);
+    double dz = 0.0;
+    if (PLANE) {
+      dz = from_sat ? pz - z1 : z1 - pz;
+      anynan |= isnan(dz);
+      sw[0] = fma(xw, dz, sw[0]);
+      sd[0] = fma(xd, dz, sd[0]);
+      if (CLOUDY) { sl[0] = fma(xl, dz, sl[0]); si[0] = fma(xi, dz, si[0]); }
+      tauprof[0] = fma(xtot, dz, tauprof[0]);
+    }
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
-      const double dsa = (a0 + a < A) ? dsp[(long long)a * L + j] : 0.0;
-      const double tw = xw * dsa;
-      const double td = xd * dsa;
-      sw[a] += tw;
-      sd[a] += td;
-      double tau = tw + td;
-      if (CLOUDY) {
-        const double tl = xl * dsa;
-        const double ti = xi * dsa;
-        sl[a] += tl;
-        si[a] += ti;
-        tau = tau + ti + tl;
+      double dsa;
+      if (PLANE) {
+        dsa = dz * amass[a];
+      } else {
+        dsa = (a0 + a < A) ? dsp[(long long)a * L + j] : 0.0;
+        sw[a] = fma(xw, dsa, sw[a]);
+        sd[a] = fma(xd, dsa, sd[a]);
+        if (CLOUDY) { sl[a] = fma(xl, dsa, sl[a]); si[a] = fma(xi, dsa, si[a]); }
       }
-      const double ex = exp(-tau);
-      const double boftlay = (bnear + bfar * ex) * rcp_fast(1.0 + ex);
+      const double tau = xtot * dsa;
+      if (!PLANE) tauprof[a] += tau;
+      const double ex = exp_nb(fmax(-tau, -700.0));
+      const double boftlay = fma(bfar, ex, bnear) * rcp_fast(1.0 + ex);
       batm[a] = fma(boftlay * trans[a], 1.0 - ex, batm[a]);
       trans[a] *= ex;
-      tauprof[a] += tau;
       if (want_tl && a0 + a == tl_angle) tau_layer[row + j] = tau;
     }
     bnear = bfar;
+    pw = xw1; pd = xd1; pl = xl1; pi_ = xi1; pz = z1;
   }
 
-  const bool bad = neg || (status && (status[p] & MWRT_ST_NAN_INPUT));  // bit set by earlier kernels
-  if (neg && status) atomicOr(&status[p], MWRT_ST_NEG_ABS);
+  const bool flagged = status && (status[p] & (MWRT_ST_NAN_INPUT | MWRT_ST_RANGE));  // earlier kernels
+  const bool bad = neg || anynan || flagged;
+  if (status && neg) atomicOr(&status[p], MWRT_ST_NEG_ABS);
+  if (status && anynan && !neg && !flagged && jf == 0 && a0 == 0) atomicOr(&status[p], MWRT_ST_NAN_INPUT);
   const double bbg = from_sat ? emis * planck_mod(hvk, tkp[0]) : planck_mod(hvk, kTCosmic);
   const long long obase = idx * (long long)A + a0;
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
     if (a0 + a >= A) break;
+    const double tp = PLANE ? tauprof[0] * amass[a] : tauprof[a];
     double boftotl, boftmr;
-    if (tauprof[a] < kExpMax) {
-      const double et = exp(-tauprof[a]);
+    if (tp < kExpMax) {
+      const double et = exp(-tp);
       boftotl = bbg * et + batm[a];
       boftmr = batm[a] / (1.0 - et);
     } else {
@@ -120,7 +171,8 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
       boftmr = batm[a];
     }
     double o_tot = bright(hvk, boftotl), o_atm = bright(hvk, batm[a]), o_mr = bright(hvk, boftmr);
-    double o_w = sw[a], o_d = sd[a], o_l = sl[a], o_i = si[a];
+    double o_w = PLANE ? sw[0] * amass[a] : sw[a], o_d = PLANE ? sd[0] * amass[a] : sd[a];
+    double o_l = PLANE ? sl[0] * amass[a] : sl[a], o_i = PLANE ? si[0] * amass[a] : si[a];
     if (bad) o_tot = o_atm = o_mr = o_w = o_d = o_l = o_i = nan("");
     if (tbtotal) tbtotal[obase + a] = o_tot;
     if (tbatm) tbatm[obase + a] = o_atm;
@@ -135,33 +187,32 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
 template <int NA>
 static int launch_rte_na(bool cloudy, int P, int L, int F, int A, const double* tk,
                          const double* awet, const double* adry, const double* aliq,
-                         const double* aice, const double* ds, const double* frq, int from_sat,
-                         double emis, double* tbtotal, double* tbatm, double* tmr, double* tauwet,
-                         double* taudry, double* tauliq, double* tauice, double* tau_layer,
-                         int tl_angle, int* status, cudaStream_t st) {
+                         const double* aice, const double* ds, const double* z, const double* amass,
+                         const double* frq, int from_sat, double emis, double* tbtotal,
+                         double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
+                         double* tauice, double* tau_layer, int tl_angle, int* status,
+                         cudaStream_t st) {
   const long long n = (long long)P * F;
   dim3 grid((unsigned)((n + kRteThreads - 1) / kRteThreads), (unsigned)((A + NA - 1) / NA));
-  if (cloudy)
-    k_rte<NA, true><<<grid, kRteThreads, 0, st>>>(P, L, F, A, tk, awet, adry, aliq, aice, ds, frq,
-                                                  from_sat, emis, tbtotal, tbatm, tmr, tauwet,
-                                                  taudry, tauliq, tauice, tau_layer, tl_angle,
-                                                  status);
-  else
-    k_rte<NA, false><<<grid, kRteThreads, 0, st>>>(P, L, F, A, tk, awet, adry, aliq, aice, ds, frq,
-                                                   from_sat, emis, tbtotal, tbatm, tmr, tauwet,
-                                                   taudry, tauliq, tauice, tau_layer, tl_angle,
-                                                   status);
+#define MWRT_K_ARGS P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, from_sat, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status
+  const bool plane = (ds == nullptr);
+  if (cloudy && plane) k_rte<NA, true, true><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);
+  else if (cloudy) k_rte<NA, true, false><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);
+  else if (plane) k_rte<NA, false, true><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);
+  else k_rte<NA, false, false><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);
+#undef MWRT_K_ARGS
   MWRT_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
+// ds != null: general path (P,A,L).  ds == null: plane-parallel, z (P,L) + amass (A,) device arrays.
 int rte_launch(int P, int L, int F, int A, const double* tk, const double* awet, const double* adry,
-               const double* aliq, const double* aice, const double* ds, const double* frq,
-               int from_sat, double emis, double* tbtotal, double* tbatm, double* tmr,
-               double* tauwet, double* taudry, double* tauliq, double* tauice, double* tau_layer,
-               int tl_angle, int* status, cudaStream_t st) {
+               const double* aliq, const double* aice, const double* ds, const double* z,
+               const double* amass, const double* frq, int from_sat, double emis, double* tbtotal,
+               double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
+               double* tauice, double* tau_layer, int tl_angle, int* status, cudaStream_t st) {
   const bool cloudy = (aliq != nullptr) && (aice != nullptr);
-#define MWRT_RTE_ARGS cloudy, P, L, F, A, tk, awet, adry, aliq, aice, ds, frq, from_sat, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, st
+#define MWRT_RTE_ARGS cloudy, P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, from_sat, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, st
   int na;
   if (A <= 1) na = 1;
   else if (A <= 2) na = 2;
