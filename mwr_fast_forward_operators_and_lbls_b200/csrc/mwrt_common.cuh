@@ -84,6 +84,89 @@ __device__ __forceinline__ double exp_nb(double x) {
   return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
+// ---- branch-free natural log ---------------------------------------------------------------------
+// log(x) for normal positive x (callers substitute 1.0 for anything else and select afterwards).
+// x = 2^e * m with m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716,
+// odd series to s^21 (truncation 2e-17).  ~22 FP64-pipe instructions + 1 MUFU, no branch.
+__device__ __forceinline__ double log_nb(double x) {
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  int e = (hi >> 20) - 1023;
+  hi = (hi & 0x000fffff) | 0x3ff00000;            // m in [1, 2)
+  const bool big = hi >= 0x3ff6a09f;              // m >= sqrt(2) (top mantissa bits)
+  hi = big ? hi - 0x00100000 : hi;                // m/2
+  e = big ? e + 1 : e;
+  const double m = __hiloint2double(hi, lo);
+  const double s = (m - 1.0) * rcp_fast(m + 1.0);
+  const double z = s * s;
+  double q = 1.0 / 21.0;
+  q = fma(q, z, 1.0 / 19.0);
+  q = fma(q, z, 1.0 / 17.0);
+  q = fma(q, z, 1.0 / 15.0);
+  q = fma(q, z, 1.0 / 13.0);
+  q = fma(q, z, 1.0 / 11.0);
+  q = fma(q, z, 1.0 / 9.0);
+  q = fma(q, z, 1.0 / 7.0);
+  q = fma(q, z, 1.0 / 5.0);
+  q = fma(q, z, 1.0 / 3.0);
+  const double s2 = s + s;
+  const double ed = (double)e;
+  // e*ln2_hi + (2s + (2s*z*q + e*ln2_lo)); ln2_hi has its low 21 bits clear so e*ln2_hi is exact
+  const double tail = fma(s2 * z, q, ed * 1.90821492927058770002e-10);
+  return fma(ed, 6.93147180369123816490e-01, s2 + tail);
+}
+
+// The same exp over N independent arguments, written stage by stage so that the N dependency chains
+// are interleaved in program order (the FP64 pipe needs ~4 independent DFMAs in flight per scheduler;
+// left to itself the compiler serialises the chains to save registers).
+template <int N>
+__device__ __forceinline__ void exp_nb_vec(const double (&x)[N], double (&y)[N]) {
+  const double kMagic = 6755399441055744.0;
+  double t[N], r[N], p[N];
+  int k[N];
+#pragma unroll
+  for (int a = 0; a < N; ++a) t[a] = fma(x[a], 1.4426950408889634, kMagic);
+#pragma unroll
+  for (int a = 0; a < N; ++a) {
+    k[a] = __double2loint(t[a]);
+    t[a] -= kMagic;
+  }
+#pragma unroll
+  for (int a = 0; a < N; ++a) r[a] = fma(-t[a], 6.93147180369123816490e-01, x[a]);
+#pragma unroll
+  for (int a = 0; a < N; ++a) r[a] = fma(-t[a], 1.90821492927058770002e-10, r[a]);
+#pragma unroll
+  for (int a = 0; a < N; ++a) p[a] = fma(1.6059043836821613e-10, r[a], 2.08767569878681e-09);
+  const double c[11] = {2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
+                        2.48015873015873e-05,  1.984126984126984e-04, 1.388888888888889e-03,
+                        8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01,
+                        0.5,                   1.0};
+#pragma unroll
+  for (int i = 0; i < 11; ++i) {
+#pragma unroll
+    for (int a = 0; a < N; ++a) p[a] = fma(p[a], r[a], c[i]);
+  }
+#pragma unroll
+  for (int a = 0; a < N; ++a) p[a] = fma(p[a], r[a], 1.0);
+#pragma unroll
+  for (int a = 0; a < N; ++a)
+    y[a] = __hiloint2double(__double2hiint(p[a]) + (k[a] << 20), __double2loint(p[a]));
+}
+
+// N reciprocals, staged like exp_nb_vec
+template <int N>
+__device__ __forceinline__ void rcp_fast_vec(const double (&x)[N], double (&y)[N]) {
+  double r[N], e[N];
+#pragma unroll
+  for (int a = 0; a < N; ++a) asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[a]) : "d"(x[a]));
+#pragma unroll
+  for (int a = 0; a < N; ++a) e[a] = fma(-x[a], r[a], 1.0);
+#pragma unroll
+  for (int a = 0; a < N; ++a) e[a] = fma(e[a], e[a], e[a]);
+#pragma unroll
+  for (int a = 0; a < N; ++a) y[a] = fma(r[a], e[a], r[a]);
+}
+
 // ---- minimal complex arithmetic (speed-dependent line shape, liquid permittivity) -----------
 struct cplx {
   double re, im;

@@ -18,20 +18,29 @@ namespace mwrt {
 constexpr int kRteThreads = 128;
 
 // One layer of exponential_integration without the ds factor: x0 = lower level,
-// x1 = upper level.  Negative input -> NaN (PyRTlib raises ValueError; the caller flags the profile
-// with MWRT_ST_NEG_ABS).
+// x1 = upper level.  Branch-free (selects) so the caller's layer loop stays one basic block:
+//   negative input -> NaN and `neg` (PyRTlib raises ValueError; the profile gets MWRT_ST_NEG_ABS)
+//   |x1-x0| < 1e-9 -> x1;  a zero endpoint -> mean (zeroflg) or 0;  else (x1-x0)/log(x1/x0).
 __device__ __forceinline__ double layer_mean(double x0, double x1, bool zeroflg, bool& neg) {
-  if (x0 < 0.0 || x1 < 0.0) {
-    neg = true;
-    return nan("");
-  }
-  if (fabs(x1 - x0) < 1e-09) return x1;
-  if (x0 == 0.0 || x1 == 0.0) return zeroflg ? (x1 + x0) * 0.5 : 0.0;
-  return (x1 - x0) / log(x1 / x0);
+  const bool negv = (x0 < 0.0) || (x1 < 0.0);
+  const bool close = fabs(x1 - x0) < 1e-09;
+  const bool zero = (x0 == 0.0) || (x1 == 0.0);
+  const bool use_log = !(negv || close || zero) && (x0 > 0.0) && (x1 > 0.0);  // false for NaN too
+  const double a = use_log ? x1 : 2.0, bq = use_log ? x0 : 1.0;              // keeps log_nb's domain
+  const double lm = div_fast(x1 - x0, log_nb(div_fast(a, bq)));
+  double r = zero ? (zeroflg ? (x1 + x0) * 0.5 : 0.0) : lm;
+  r = close ? x1 : r;
+  r = (negv || !(use_log || close || zero)) ? nan("") : r;
+  neg = neg || negv;
+  return r;
 }
 
-// modified Planck function 1/(exp(hvk/T) - 1); hvk/T is O(1e-2) for microwave frequencies
-__device__ __forceinline__ double planck_mod(double hvk, double t) { return 1.0 / (exp(hvk / t) - 1.0); }
+// modified Planck function 1/(exp(hvk/T) - 1); hvk/T is O(1e-2) for microwave frequencies.
+// T is a physical temperature here (kernel 1 flags anything outside 50..1000 K), hvk/T < 700.
+__device__ __forceinline__ double planck_mod(double hvk, double t) {
+  const double x = div_fast(hvk, t);
+  return rcp_fast(exp_nb(fmax(fmin(x, 700.0), -700.0)) - 1.0);
+}
 __device__ __forceinline__ double bright(double hvk, double b) {
   if (b > 0.0 || isnan(b)) return hvk / log(1.0 + 1.0 / b);
   return 0.0;
@@ -42,7 +51,10 @@ __device__ __forceinline__ double bright(double hvk, double b) {
 // measured on B200 (profiles/r01b_*): the plane-parallel variant is fastest capped at 128 registers
 // (4 CTAs/SM); the general variant spills there and runs best uncapped
 template <int NA, bool CLOUDY, bool PLANE>
-__global__ void __launch_bounds__(kRteThreads, (PLANE && !CLOUDY) ? 4 : 1)
+#ifndef MWRT_RTE_MINB
+#define MWRT_RTE_MINB 4
+#endif
+__global__ void __launch_bounds__(kRteThreads, (PLANE && !CLOUDY) ? MWRT_RTE_MINB : 1)
 k_rte(const int P, const int L, const int F, const int A, const double* __restrict__ tk,
       const double* __restrict__ awet, const double* __restrict__ adry,
       const double* __restrict__ aliq, const double* __restrict__ aice,
@@ -63,7 +75,7 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
   const double* dsp = PLANE ? nullptr : ds + (p * A + a0) * (long long)L;
   const double hvk = (frq[jf] * 1e9) * kPlanckH / kBoltzmannK;
 
-  double batm[NA], trans[NA], amass[NA];
+  double batm[NA], trans[NA], amass[NA];  // (amass in shared memory measured slower)
   // species sums: per angle in the general case, one zenith-path sum (scaled at the end) if PLANE
   constexpr int NS = PLANE ? 1 : NA;
   double sw[NS], sd[NS], sl[NS], si[NS], tauprof[NS];
@@ -80,54 +92,76 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
   const bool want_tl = (tau_layer != nullptr) && (tl_angle >= a0) && (tl_angle < a0 + NA);
   if (want_tl) tau_layer[row] = 0.0;
   const int dir = from_sat ? -1 : 1;
-  int lev = from_sat ? L - 1 : 0;       // level sequence starts at the observer's end
+  const int lev0 = from_sat ? L - 1 : 0;   // level sequence starts at the observer's end
+  const double zref = PLANE ? zp[0] : 0.0;
 
-  // "prev" = level already passed (nearer to the observer); "cur" = next level, loaded one step ahead
-  double pw = awet[row + lev], pd = adry[row + lev];
-  double pl = 0.0, pi_ = 0.0;
-  if (CLOUDY) { pl = aliq[row + lev]; pi_ = aice[row + lev]; }
-  double pz = PLANE ? zp[lev] - zp[0] : 0.0;
-  double bnear = planck_mod(hvk, tkp[lev]);
-  int nlev = lev + dir;
-  double cw = awet[row + nlev], cd = adry[row + nlev], ct = tkp[nlev];
-  double cl = 0.0, ci = 0.0, cz = 0.0;
-  if (CLOUDY) { cl = aliq[row + nlev]; ci = aice[row + nlev]; }
-  if (PLANE) cz = zp[nlev] - zp[0];
+  // Software pipeline over the level sequence lev0, lev0+dir, ...:
+  //   A = level reached last, B = level being reached (already in registers), C = prefetched.
+  // The scalars of the NEXT layer (2-4 layer means, 1 Planck term: serial log/exp chains) are
+  // computed in the same basic block as the CURRENT layer's NA-angle stage, so they overlap.
+  struct Lvl { double w, d, l, i, t, z; };
+  struct Lay { double xw, xd, xl, xi, xtot, bfar, dz; };
+  auto load = [&](int lv) {
+    Lvl v;
+    v.w = awet[row + lv];
+    v.d = adry[row + lv];
+    v.l = CLOUDY ? aliq[row + lv] : 0.0;
+    v.i = CLOUDY ? aice[row + lv] : 0.0;
+    v.t = tkp[lv];
+    v.z = PLANE ? zp[lv] - zref : 0.0;
+    return v;
+  };
+  auto prep = [&](const Lvl& nr, const Lvl& fr, bool& ng, bool& nn) {
+    // nr = level nearer to the observer, fr = farther; lower/upper depends on the direction
+    const Lvl& lo = from_sat ? fr : nr;
+    const Lvl& up = from_sat ? nr : fr;
+    Lay y;
+    y.xw = layer_mean(lo.w, up.w, true, ng);
+    y.xd = layer_mean(lo.d, up.d, true, ng);
+    y.xtot = y.xw + y.xd;
+    y.xl = 0.0;
+    y.xi = 0.0;
+    if (CLOUDY) {
+      y.xl = layer_mean(lo.l, up.l, false, ng);
+      y.xi = layer_mean(lo.i, up.i, false, ng);
+      y.xtot = y.xtot + y.xi + y.xl;
+    }
+    y.bfar = planck_mod(hvk, fr.t);
+    y.dz = up.z - lo.z;
+    nn = nn || isnan(y.xtot) || isnan(fr.t) || isnan(y.dz);
+    return y;
+  };
+
+  Lvl lvA = load(lev0);
+  anynan = isnan(lvA.t);
+  double bnear = planck_mod(hvk, lvA.t);
+  Lvl lvB = load(lev0 + dir);
+  Lay cur = prep(lvA, lvB, neg, anynan);
+  lvA = lvB;
+  lvB = load(L > 2 ? lev0 + 2 * dir : lev0 + dir);
 
   for (int step = 1; step < L; ++step) {
-    const int clev = nlev;                       // level reached in this step
+    const int clev = lev0 + step * dir;          // level reached in this step
     const int j = from_sat ? clev + 1 : clev;    // layer index (upper level of the layer)
-    const double xw1 = cw, xd1 = cd, xl1 = cl, xi1 = ci, t1 = ct, z1 = cz;
-    // prefetch the following level while this layer is integrated
-    nlev = clev + dir;
-    const int ld = (step + 1 < L) ? nlev : clev;
-    cw = awet[row + ld];
-    cd = adry[row + ld];
-    ct = tkp[ld];
-    if (CLOUDY) { cl = aliq[row + ld]; ci = aice[row + ld]; }
-    if (PLANE) cz = zp[ld] - zp[0];
+    // next layer's scalars (discarded after the last step) + prefetch of the level after it
+    bool ng2 = false, nn2 = false;
+    const Lay nxt = prep(lvA, lvB, ng2, nn2);
+    const bool more = step + 1 < L;
+    neg = neg || (more && ng2);
+    anynan = anynan || (more && nn2);
+    lvA = lvB;
+    lvB = load(step + 2 < L ? lev0 + (step + 2) * dir : clev);
 
-    // layer_mean(lower level, upper level): in downwelling order prev is the lower level
-    const double xw = from_sat ? layer_mean(xw1, pw, true, neg) : layer_mean(pw, xw1, true, neg);
-    const double xd = from_sat ? layer_mean(xd1, pd, true, neg) : layer_mean(pd, xd1, true, neg);
-    double xtot = xw + xd;
-    double xl = 0.0, xi = 0.0;
-    if (CLOUDY) {
-      xl = from_sat ? layer_mean(xl1, pl, false, neg) : layer_mean(pl, xl1, false, neg);
-      xi = from_sat ? layer_mean(xi1, pi_, false, neg) : layer_mean(pi_, xi1, false, neg);
-      xtot = xtot + xi + xl;
-    }
-    anynan |= isnan(xtot);
-    const double bfar = planck_mod(hvk, t1);
-    double dz = 0.0;
+    const double xw = cur.xw, xd = cur.xd, xl = cur.xl, xi = cur.xi, xtot = cur.xtot;
+    const double bfar = cur.bfar, dz = cur.dz;
     if (PLANE) {
-      dz = from_sat ? pz - z1 : z1 - pz;
-      anynan |= isnan(dz);
       sw[0] = fma(xw, dz, sw[0]);
       sd[0] = fma(xd, dz, sd[0]);
       if (CLOUDY) { sl[0] = fma(xl, dz, sl[0]); si[0] = fma(xi, dz, si[0]); }
       tauprof[0] = fma(xtot, dz, tauprof[0]);
     }
+    // per-angle work, written stage by stage over the NA angles (see exp_nb_vec)
+    double tau[NA], ntau[NA], ex[NA], den[NA], rden[NA];
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       double dsa;
@@ -139,16 +173,30 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
         sd[a] = fma(xd, dsa, sd[a]);
         if (CLOUDY) { sl[a] = fma(xl, dsa, sl[a]); si[a] = fma(xi, dsa, si[a]); }
       }
-      const double tau = xtot * dsa;
-      if (!PLANE) tauprof[a] += tau;
-      const double ex = exp_nb(fmax(-tau, -700.0));
-      const double boftlay = fma(bfar, ex, bnear) * rcp_fast(1.0 + ex);
-      batm[a] = fma(boftlay * trans[a], 1.0 - ex, batm[a]);
-      trans[a] *= ex;
-      if (want_tl && a0 + a == tl_angle) tau_layer[row + j] = tau;
+      tau[a] = xtot * dsa;
+      if (!PLANE) tauprof[a] += tau[a];
+    }
+#pragma unroll
+    for (int a = 0; a < NA; ++a) ntau[a] = fmax(-tau[a], -700.0);
+    exp_nb_vec<NA>(ntau, ex);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) den[a] = 1.0 + ex[a];
+    rcp_fast_vec<NA>(den, rden);
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      const double boftlay = fma(bfar, ex[a], bnear) * rden[a];
+      batm[a] = fma(boftlay * trans[a], 1.0 - ex[a], batm[a]);
+      trans[a] *= ex[a];
+    }
+    if (want_tl) {
+      double tl = 0.0;
+#pragma unroll
+      for (int a = 0; a < NA; ++a)
+        if (a0 + a == tl_angle) tl = tau[a];
+      tau_layer[row + j] = tl;
     }
     bnear = bfar;
-    pw = xw1; pd = xd1; pl = xl1; pi_ = xi1; pz = z1;
+    cur = nxt;
   }
 
   const bool flagged = status && (status[p] & (MWRT_ST_NAN_INPUT | MWRT_ST_RANGE));  // earlier kernels
