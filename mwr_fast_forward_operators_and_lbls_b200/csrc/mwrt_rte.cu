@@ -52,7 +52,7 @@ __device__ __forceinline__ double bright(double hvk, double b) {
 // (4 CTAs/SM); the general variant spills there and runs best uncapped
 template <int NA, bool CLOUDY, bool PLANE>
 #ifndef MWRT_RTE_MINB
-#define MWRT_RTE_MINB 4
+#define MWRT_RTE_MINB 3
 #endif
 __global__ void __launch_bounds__(kRteThreads, (PLANE && !CLOUDY) ? MWRT_RTE_MINB : 1)
 k_rte(const int P, const int L, const int F, const int A, const double* __restrict__ tk,

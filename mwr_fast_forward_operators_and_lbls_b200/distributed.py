@@ -55,6 +55,65 @@ def gather_outputs(out, P_total, fields=None, group=None):
     return {k: full[:, i] for i, k in enumerate(fields)}
 
 
+class OverlappedForward:
+    """Compute the local shard in `nchunk` pieces and all-gather each piece on a side stream while
+    the next piece is being computed, so the final gather hides behind the kernels.
+
+    Result layout: `gathered[c]` is a (world, Pc, nfield, F, A) tensor holding chunk c of every
+    rank; `field(name)` assembles the contiguous (P_total, F, A) view order (rank-major, then local
+    index) on demand.  Equal shard sizes are required (weak-scaling batches); use `simulate_sharded`
+    for ragged shards.
+    """
+
+    def __init__(self, plan, P_local, fields, nchunk=2, group=None):
+        self.plan, self.fields, self.group = plan, tuple(fields), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.P_local = int(P_local)
+        self.nchunk = max(1, min(int(nchunk), self.P_local))
+        base, rem = divmod(self.P_local, self.nchunk)
+        self.bounds = []
+        a = 0
+        for c in range(self.nchunk):
+            b = a + base + (1 if c < rem else 0)
+            self.bounds.append((a, b))
+            a = b
+        nf, F, A = len(self.fields), plan.Fo, plan.A
+        dev = torch.device("cuda", torch.cuda.current_device())
+        # local results, field-stacked per chunk so that one collective moves all fields of a chunk
+        self.local = [torch.empty((nf, b - a, F, A), dtype=torch.float64, device=dev)
+                      for a, b in self.bounds]
+        self.status = torch.empty((self.P_local,), dtype=torch.int32, device=dev)
+        self.gathered = [torch.empty((self.world,) + tuple(t.shape), dtype=torch.float64, device=dev)
+                         for t in self.local]
+        self.comm = torch.cuda.Stream()
+        self.events = [torch.cuda.Event() for _ in self.bounds]
+
+    def run(self, z, p, t, rh, denliq=None, denice=None):
+        main = torch.cuda.current_stream()
+        self.comm.wait_stream(main)          # previous consumers of `gathered` are ordered before us
+        for c, (a, b) in enumerate(self.bounds):
+            out = {k: self.local[c][i] for i, k in enumerate(self.fields)}
+            out["status"] = self.status[a:b]
+            self.plan.forward(z[a:b], p[a:b], t[a:b], rh[a:b],
+                              None if denliq is None else denliq[a:b],
+                              None if denice is None else denice[a:b], fields=self.fields, out=out)
+            self.events[c].record(main)
+            if self.world > 1:
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(self.events[c])
+                    dist.all_gather_into_tensor(self.gathered[c], self.local[c], group=self.group)
+            else:
+                self.gathered[c] = self.local[c].unsqueeze(0)
+        main.wait_stream(self.comm)
+        return self
+
+    def field(self, name):
+        """(P_total, F, A) tensor of one field, profiles ordered rank-major."""
+        i = self.fields.index(name)
+        return torch.cat([g[:, i] for g in self.gathered], dim=1).reshape(
+            self.world * self.P_local, self.plan.Fo, self.plan.A)
+
+
 def simulate_sharded(plan, z, p, t, rh, denliq=None, denice=None, fields=None, group=None):
     """Every rank passes the FULL (P,L) device tensors (or identical copies); each computes its block
     and all ranks return the assembled (P,F,A) results."""
