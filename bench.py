@@ -250,11 +250,18 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None   # measured DRAM bytes per launch from the committed ncu --set full capture
+    try:
+        if args.model == MODEL:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_absorption"]["traffic_bytes"]
+    except Exception:
+        pass
     roof = {"bound": "fp64", "kernel": "k_absorption", "achieved": achieved,
             "peak": peak_flops / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak_flops / 1e12),
             "peak_source": "self-measured DFMA stream in this run (nominal 37.2); MEASURED_PEAKS.json "
                            "has no fp64 figure",
-            "traffic": None, "kernel_ms": k_ms,
+            "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_traffic.json)",
+            "kernel_ms": k_ms,
             "kernel_share_of_step": k_ms / (total_ms / args.steps),
             "algorithmic_flops_per_launch": w["flops_k_abs"],
             "hbm": {"algorithmic_bytes_per_launch": w["bytes_k_abs"],
