@@ -171,6 +171,13 @@ int mwrt_plan_forward_device(mwrt_plan* plan, int P, const mwrt_profiles* in, co
  * batch, overlaps H2D / kernels / D2H on the plan's streams, and returns after everything landed. */
 int mwrt_plan_forward_host(mwrt_plan* plan, int P, const mwrt_profiles* in, const mwrt_outputs* out);
 
+/* ---- next to the path: model-minus-reference statistics -------------------
+ * stats_by_channel (/root/reference/python_src/plot_scripts/multi_campaign_plots_and_ana.py:155-178)
+ * for M independent columns (channel x elevation x ...): values, refs (T,M) device; outputs (M,) device.
+ * n_valid counts the non-NaN MODEL values (as the reference does); NaN deviations are skipped. */
+int mwrt_stats_f64(int T, int64_t M, const double* values, const double* refs, double* bias,
+                   double* std, double* rmse, double* n_valid, void* stream);
+
 /* ---- measurement helper: dependent-free DFMA stream, returns achieved fp64 FLOP/s (2 per DFMA).
  * bench.py uses it as the denominator "of self-measured DFMA peak" (MEASURED_PEAKS.json has no fp64
  * figure).  Synchronises. */

@@ -68,6 +68,7 @@ SYMBOLS = {
                                            C.POINTER(Outputs), C.c_void_p]),
     "mwrt_plan_forward_host": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Profiles),
                                          C.POINTER(Outputs)]),
+    "mwrt_stats_f64": (C.c_int, [C.c_int, C.c_int64] + [C.c_void_p] * 7),
     "mwrt_measure_dfma_peak": (C.c_int, [c_dp, c_dp]),
 }
 

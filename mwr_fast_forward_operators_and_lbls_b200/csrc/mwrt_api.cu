@@ -42,6 +42,8 @@ int slant_path_launch(int P, int L, int A, const double* z, const double* p, con
 int bandpass_launch(int P, int C, int S, int A, const double* in, const double* w, double* out,
                     cudaStream_t st);
 int dfma_peak(double* flops, double* mhz);
+int stats_launch(int T, long long M, const double* values, const double* refs, double* bias,
+                 double* sd, double* rmse, double* nvalid, cudaStream_t st);
 
 struct mwrt_builtin_model {
   const char* name;
@@ -492,6 +494,13 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
   MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_d2h));
   MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_comp));
   return 0;
+}
+
+int mwrt_stats_f64(int T, int64_t M, const double* values, const double* refs, double* bias,
+                   double* std, double* rmse, double* n_valid, void* stream) {
+  if (T <= 0 || M <= 0 || !values || !refs || !bias || !std || !rmse)
+    return fail_arg(MWRT_E_ARG, "mwrt_stats_f64: bad argument");
+  return stats_launch(T, M, values, refs, bias, std, rmse, n_valid, (cudaStream_t)stream);
 }
 
 int mwrt_measure_dfma_peak(double* flops_per_s, double* sm_clock_mhz_est) {

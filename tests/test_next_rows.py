@@ -1,0 +1,162 @@
+"""N2 wire formats + the batched driver, N4 statistics.  CPU tests cover the
+formats and the oracle ports; the GPU tests check the CUDA path against those ports."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import postproc
+
+
+def _synth_level_dataset(T=3, C=2, L=24, seed=5):
+    """A tiny stand-in for MWR_rs_..._all_elevations.nc: Level_* (N_Levels, time, Crop), top-first."""
+    import mwr_fast_forward_operators_and_lbls_b200 as pkg
+    d = pkg.synth_profiles(T * C, L, seed=seed)
+
+    def lay(v, mul):   # (T*C, L) ground-first -> (L, T, C) top-first
+        return np.ascontiguousarray((v * mul).T[::-1].reshape(L, T, C))
+    return dict(Level_z=lay(d["z"], 1000.0), Level_Pressure=lay(d["p"], 1.0),
+                Level_Temperature=lay(d["t"], 1.0), Level_RH=lay(d["rh"], 100.0))
+
+
+def test_legacy_csv_roundtrip(tmp_path):
+    from mwr_fast_forward_operators_and_lbls_b200 import io_formats as io
+    rng = np.random.default_rng(0)
+    crop = {m: rng.uniform(10, 290, 14) for m in io.LEGACY_MODELS}
+    full = {m: rng.uniform(10, 290, 14) for m in io.LEGACY_MODELS}
+    path = str(tmp_path / "sonde_out.txt")
+    df = io.write_legacy_csv(path, crop, full)
+    assert len(df) == 252 and list(df.columns) == ["tbtotal"]
+    # the consumer's slicing (old_merge2nc.py:417-435)
+    import pandas as pd
+    prl = pd.read_csv(path)["tbtotal"].values
+    assert np.allclose(prl[0:14], crop["R17"]) and np.allclose(prl[112:126], crop["R24"])
+    assert np.allclose(prl[126:140], full["R17"]) and np.allclose(prl[238:252], full["R24"])
+    c2, f2 = io.read_legacy_csv(path)
+    assert all(np.allclose(c2[m], crop[m]) and np.allclose(f2[m], full[m]) for m in io.LEGACY_MODELS)
+
+
+def test_netcdf_contract_roundtrip(tmp_path):
+    from mwr_fast_forward_operators_and_lbls_b200 import io_formats as io
+    lv = _synth_level_dataset()
+    ds = io.SimpleDataset({k: (("N_Levels", "time", "Crop"), v) for k, v in lv.items()})
+    ds["elevation"] = (("elevation",), np.array([90., 30., 4.2]))
+    tb = np.random.default_rng(1).uniform(10, 290, (3, 14, 3, 2))
+    for model, var in io.OUTPUT_VARS:
+        ds[var] = (io.TB_DIMS, tb)
+        ds[var].attrs = io.tb_attrs(model)
+    path = str(tmp_path / "out.nc")
+    ds.to_netcdf(path, format="NETCDF4_CLASSIC")
+    back = io.open_dataset(path)
+    for model, var in io.OUTPUT_VARS:
+        assert tuple(back[var].dims) == ("time", "N_Channels", "elevation", "Crop")
+        assert np.array_equal(np.asarray(back[var].values), tb)
+        assert back[var].attrs["units"] == "K"
+        assert back[var].attrs["long_name"] == "Brightness temperature modelled by %s" % model
+        assert back[var].attrs["standard_name"] == "brightness_temperature"
+    assert np.array_equal(np.asarray(back["Level_z"].values), lv["Level_z"])
+
+
+def test_stats_oracle_matches_definition():
+    rng = np.random.default_rng(2)
+    v = rng.normal(150, 30, (40, 14))
+    r = v + rng.normal(0.3, 1.0, v.shape)
+    v[3, 2] = np.nan
+    r[7, 5] = np.nan
+    sd, bias, rmse = postproc.stats_by_channel(v, r, 14)
+    d = v[:, 0] - r[:, 0]
+    assert np.isclose(bias[0], d.mean()) and np.isclose(rmse[0], np.sqrt((d ** 2).mean()))
+    assert np.isclose(sd[0], d.std())
+    # reference quirk: n_valid counts the model values only
+    d5 = v[:, 5] - r[:, 5]
+    assert np.isclose(bias[5], np.nansum(d5) / 40)
+
+
+@pytest.mark.gpu
+def test_stats_gpu_vs_oracle(built_lib):
+    from mwr_fast_forward_operators_and_lbls_b200 import stats
+    rng = np.random.default_rng(3)
+    v = rng.normal(150, 30, (521, 14, 10))
+    r = v + rng.normal(0.3, 1.0, v.shape)
+    v[rng.uniform(size=v.shape) < 0.02] = np.nan
+    r[rng.uniform(size=v.shape) < 0.02] = np.nan
+    sd, bias, rmse = stats.stats_by_channel(v, r, 14)
+    for k in range(10):
+        o_sd, o_bias, o_rmse = postproc.stats_by_channel(v[:, :, k], r[:, :, k], 14)
+        assert np.allclose(sd.cpu().numpy()[:, k], o_sd, rtol=1e-12, atol=0)
+        assert np.allclose(bias.cpu().numpy()[:, k], o_bias, rtol=1e-10, atol=1e-13)
+        assert np.allclose(rmse.cpu().numpy()[:, k], o_rmse, rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
+def test_batched_driver_equals_reference_loop(built_lib, tmp_path):
+    """derive_TBs4PyRTlib: four batched GPU calls == the reference's triple loop (oracle port),
+    including the per-profile NaN gate and the output variable contract."""
+    from mwr_fast_forward_operators_and_lbls_b200 import driver, io_formats as io
+    import mwr_fast_forward_operators_and_lbls_b200 as pkg
+    lv = _synth_level_dataset(T=2, C=2, L=20)
+    lv["Level_Temperature"][5, 1, 0] = np.nan           # one NaN profile (time 1, Crop 0)
+    elev = np.array([90., 19.2, 4.2])
+    ref = postproc.derive_TBs4PyRTlib_loop(lv["Level_z"], lv["Level_Pressure"], lv["Level_Temperature"],
+                                           lv["Level_RH"], elev, pkg.HATPRO_FRQ)
+    ds = io.SimpleDataset({k: (("N_Levels", "time", "Crop"), v) for k, v in lv.items()})
+    ds["elevation"] = (("elevation",), elev)
+    ds = driver.derive_TBs4PyRTlib(ds, None)
+    for model, var in io.OUTPUT_VARS:
+        got = ds[var].values
+        assert got.shape == (2, 14, 3, 2) and ds[var].dims == io.TB_DIMS
+        assert np.isnan(got[1, :, :, 0]).all() and np.isnan(ref[model][1, :, :, 0]).all()
+        ok = ~np.isnan(ref[model])
+        assert np.array_equal(ok, ~np.isnan(got))
+        assert np.max(np.abs(got[ok] - ref[model][ok])) < 1e-3
+        assert ds[var].attrs["units"] == "K"
+    # CLI round trip (-i/-o like the reference)
+    src, dst = str(tmp_path / "in.nc"), str(tmp_path / "out.nc")
+    ds_in = io.SimpleDataset({k: (("N_Levels", "time", "Crop"), v) for k, v in lv.items()})
+    ds_in["elevation"] = (("elevation",), elev)
+    ds_in.to_netcdf(src)
+    driver.main(["-i", src, "-o", dst])
+    back = io.open_dataset(dst)
+    assert np.allclose(np.asarray(back["TBs_PyRTlib_R24"].values), ds["TBs_PyRTlib_R24"].values,
+                       equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_legacy_sonde_table(built_lib, tmp_path):
+    from mwr_fast_forward_operators_and_lbls_b200 import driver, io_formats as io
+    import mwr_fast_forward_operators_and_lbls_b200 as pkg
+    from oracle import pyrtlib_vec as pv
+    d = pkg.synth_profiles(1, 30, seed=9)
+    z, p, t, rh = (d[k][0] for k in ("z", "p", "t", "rh"))
+    crop, full = driver.legacy_sonde_table(z, p, t, rh, z[2:], p[2:], t[2:], rh[2:])
+    path = str(tmp_path / "x_out.txt")
+    io.write_legacy_csv(path, crop, full)
+    c2, f2 = io.read_legacy_csv(path)
+    for m in ("R17", "R98", "R24"):
+        ref = pv.simulate(z[None], p[None], t[None], rh[None], pkg.HATPRO_FRQ, [90.0], m)["tbtotal"][0, :, 0]
+        assert np.max(np.abs(f2[m] - ref)) < 1e-3
+
+
+@pytest.mark.gpu
+def test_cloudy_wiring_from_level_liquid(built_lib):
+    """N3: Level_Liquid / Level_Ice [kg/kg] -> g m^-3 -> cloudy path; against the oracle."""
+    from mwr_fast_forward_operators_and_lbls_b200 import driver
+    import mwr_fast_forward_operators_and_lbls_b200 as pkg
+    from oracle import pyrtlib_vec as pv
+    T, C, L = 3, 2, 40
+    d = pkg.synth_profiles(T * C, L, seed=12, clouds=True)
+    rho = d["p"] * 100.0 / 287.06 / d["t"]                     # kg m^-3
+    liq_kgkg = d["denliq"] / 1000.0 / rho                      # what preprocessing stores
+
+    def lay(v, mul=1.0):
+        return np.ascontiguousarray((v * mul).T[::-1].reshape(L, T, C))
+    elev = np.array([90.0, 5.4])
+    got = driver.derive_tbs_arrays(lay(d["z"], 1000.0), lay(d["p"]), lay(d["t"]), lay(d["rh"], 100.0),
+                                   elevations=elev, models=("R24",), level_liquid=lay(liq_kgkg))["R24"]
+    denliq = driver.water_content_to_density(liq_kgkg, d["p"], d["t"])
+    assert np.allclose(denliq, d["denliq"], rtol=1e-12, atol=1e-15)
+    ref = pv.simulate(d["z"] * 1000.0 / 1000.0, d["p"], d["t"], d["rh"] * 100.0 / 100.0, pkg.HATPRO_FRQ,
+                      elev, "R24", denliq=denliq, denice=np.zeros_like(denliq))["tbtotal"]
+    ref = ref.reshape(T, C, 14, 2).transpose(0, 2, 3, 1)
+    assert (d["denliq"] > 0).any()
+    assert np.max(np.abs(got - ref)) < 1e-3
