@@ -119,8 +119,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default=MODEL)
-    ap.add_argument("--gather-chunks", type=int, default=2,
-                    help="N>1: pieces of the local shard whose all-gather overlaps the next piece's kernels")
+    ap.add_argument("--gather-chunks", type=int, default=0,
+                    help="N>1: 0 = gather of step s overlaps the kernels of step s+1 (default); k>0 = "
+                         "within-step overlap over k pieces of the local shard")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -131,7 +132,7 @@ def main():
     import torch.distributed as dist
     import mwr_fast_forward_operators_and_lbls_b200 as pkg
     from mwr_fast_forward_operators_and_lbls_b200 import _lib, roofline
-    from mwr_fast_forward_operators_and_lbls_b200.distributed import OverlappedForward
+    from mwr_fast_forward_operators_and_lbls_b200.distributed import OverlappedForward, PipelinedForward
     from mwr_fast_forward_operators_and_lbls_b200.forward import _ptr, _stream
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -157,10 +158,16 @@ def main():
     out["status"] = torch.empty((P,), dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
 
-    ovl = OverlappedForward(plan, P, fields, nchunk=args.gather_chunks) if N > 1 else None
+    # N>1: the steps are a stream of batches; the all-gather of step s (six outputs, one collective)
+    # runs on a side stream while step s+1 computes (double-buffered).  --gather-chunks > 0 selects the
+    # within-step form instead (chunk c+1 computed while chunk c travels).
+    ovl = None
+    if N > 1:
+        ovl = (OverlappedForward(plan, P, fields, nchunk=args.gather_chunks) if args.gather_chunks > 0
+               else PipelinedForward(plan, P, fields))
 
     def step():
-        if N > 1:   # shard compute + all-gather of the six outputs, chunk c+1 computed while c travels
+        if N > 1:
             return ovl.run(dev["z"], dev["p"], dev["t"], dev["rh"])
         return plan.forward(dev["z"], dev["p"], dev["t"], dev["rh"], fields=fields, out=out)
 
@@ -185,15 +192,26 @@ def main():
         e0.record()
         res = step()
         e1.record()
+    # tail: the last step's gather must have landed before the clock stops
+    tail0, tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tail0.record()
+    if isinstance(ovl, PipelinedForward):
+        ovl.finish()
+    tail1.record()
     barrier()
     t_wall1 = time.time()
-    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev] + [tail0.elapsed_time(tail1)]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
     if N > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = N * P * F * A * args.steps / (total_ms * 1e-3)
-    checksum = float((res.field("tbtotal") if N > 1 else res["tbtotal"]).sum().item())
+    if isinstance(ovl, PipelinedForward):
+        checksum = float(ovl.field("tbtotal", res).sum().item())
+    elif N > 1:
+        checksum = float(res.field("tbtotal").sum().item())
+    else:
+        checksum = float(res["tbtotal"].sum().item())
 
     # ---- end to end through the host entry point (pinned host memory, copies inside the timing)
     hin = {k: torch.from_numpy(d[k]).pin_memory() for k in keys}
@@ -285,15 +303,18 @@ def main():
             "config": {"workload": WORKLOAD, "model": args.model, "profiles_per_gpu": P, "levels": L,
                        "channels": F, "elevations": A, "parallelism": "profiles sharded by rank (dp%d)" % N,
                        "outputs": list(fields),
-                       "collective": ("all_gather_into_tensor of the stacked outputs, %d chunks overlapped with compute"
-                                      % args.gather_chunks) if N > 1 else "none",
+                       "collective": ("none" if N == 1 else
+                                      "one all_gather_into_tensor of the six stacked outputs per step, "
+                                      + ("overlapped with the next step's kernels (double-buffered); the last "
+                                         "step's gather is inside the timed total" if args.gather_chunks <= 0
+                                         else "%d chunks overlapped within the step" % args.gather_chunks)),
                        "l2": "256 MiB flush between timed steps, outside the CUDA-event pairs",
                        "timing": "sum of per-step CUDA-event intervals, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "Plan.forward_host -> mwrt_plan_forward_host (pinned host buffers)"},
-            "gpu_launches": args.steps * (plan.launch_count(P) * (args.gather_chunks if N > 1 else 1)),
+            "gpu_launches": args.steps * (plan.launch_count(P) * (args.gather_chunks if (N > 1 and args.gather_chunks > 0) else 1)),
             "roofline": roof, "cpu_baseline": cpu, "checksum_tbtotal": checksum,
             "max_abs_dtb_vs_oracle_K": "see tests/test_gpu_parity.py (1e-3 K gate; measured ~1e-11)"}
     print(json.dumps(line), flush=True)

@@ -114,6 +114,55 @@ class OverlappedForward:
             self.world * self.P_local, self.plan.Fo, self.plan.A)
 
 
+class PipelinedForward:
+    """Streaming form for a sequence of batches (steps): the all-gather of step s runs on a side
+    stream WHILE step s+1 is being computed (double-buffered results), so in steady state a step
+    costs max(compute, gather) instead of their sum.  `finish()` makes the current stream wait for
+    the last gather; results of step s are in `gathered[s % 2]`, laid out (world, nfield, P_local, F, A).
+    """
+
+    def __init__(self, plan, P_local, fields, group=None):
+        self.plan, self.fields, self.group = plan, tuple(fields), group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.P_local = int(P_local)
+        nf, F, A = len(self.fields), plan.Fo, plan.A
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.local = [torch.empty((nf, self.P_local, F, A), dtype=torch.float64, device=dev) for _ in range(2)]
+        self.status = [torch.empty((self.P_local,), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.gathered = [torch.empty((self.world, nf, self.P_local, F, A), dtype=torch.float64, device=dev)
+                         for _ in range(2)]
+        self.comm = torch.cuda.Stream()
+        self.computed = [torch.cuda.Event() for _ in range(2)]
+        self.gathered_ev = [torch.cuda.Event() for _ in range(2)]
+        self.step = 0
+
+    def run(self, z, p, t, rh, denliq=None, denice=None):
+        s = self.step % 2
+        main = torch.cuda.current_stream()
+        if self.step >= 2:
+            main.wait_event(self.gathered_ev[s])      # slot s is free once its previous gather is done
+        out = {k: self.local[s][i] for i, k in enumerate(self.fields)}
+        out["status"] = self.status[s]
+        self.plan.forward(z, p, t, rh, denliq, denice, fields=self.fields, out=out)
+        self.computed[s].record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.computed[s])
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.gathered[s], self.local[s], group=self.group)
+            else:
+                self.gathered[s][0].copy_(self.local[s])
+            self.gathered_ev[s].record(self.comm)
+        self.step += 1
+        return s
+
+    def finish(self):
+        torch.cuda.current_stream().wait_stream(self.comm)
+
+    def field(self, name, slot):
+        i = self.fields.index(name)
+        return self.gathered[slot][:, i].reshape(self.world * self.P_local, self.plan.Fo, self.plan.A)
+
+
 def simulate_sharded(plan, z, p, t, rh, denliq=None, denice=None, fields=None, group=None):
     """Every rank passes the FULL (P,L) device tensors (or identical copies); each computes its block
     and all ranks return the assembled (P,F,A) results."""
