@@ -27,17 +27,68 @@ constexpr int kAbsThreads = 128;
 
 // rare-path helpers are kept out of line: the hot loops must stay small enough for the
 // instruction caches (the first version inlined them 14x and stalled on instruction fetch)
+// Speed-dependent shapes with division-free complex arithmetic (reciprocals via MUFU + Newton, no
+// IEEE slow-path calls, no branches): the 22 GHz line takes this path for every K-band channel in the
+// lower troposphere, so it is not that rare (profiles/r01d: ~20 % of the kernel before this rewrite).
+__device__ __forceinline__ cplx cdiv_f(cplx a, cplx b) {
+  const double r = rcp_fast(fma(b.re, b.re, b.im * b.im));
+  return cplx{fma(a.re, b.re, a.im * b.im) * r, fma(a.im, b.re, -a.re * b.im) * r};
+}
+__device__ __forceinline__ double sqrt_f(double x) {  // x > 0, normal
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double h = 0.5 * y, s = x * y;
+  double e = fma(-s, h, 0.5);
+  s = fma(s, e, s);
+  h = fma(h, e, h);
+  e = fma(-s, h, 0.5);
+  s = fma(s, e, s);
+  h = fma(h, e, h);
+  return fma(fma(-s, s, x), h, s);
+}
+__device__ __forceinline__ cplx csqrt_f(cplx z) {  // principal root, z != 0
+  const double m = sqrt_f(fma(z.re, z.re, z.im * z.im));
+  const double t = sqrt_f(0.5 * (m + fabs(z.re)));
+  const double o = 0.5 * z.im * rcp_fast(t);
+  return (z.re >= 0.0) ? cplx{t, o} : cplx{fabs(o), copysign(t, z.im)};
+}
+// w(x + i y) for y >= 0 (always the case below: y = Re sqrt(.) >= 0)
+__device__ __forceinline__ cplx dcerror_f(double x, double y) {
+  const double a0 = 122.607931777104326, a1 = 214.382388694706425, a2 = 181.928533092181549,
+               a3 = 93.155580458138441, a4 = 30.180142196210589, a5 = 5.912626209773153,
+               a6 = 0.564189583562615;
+  const double b0 = 122.607931773875350, b1 = 352.730625110963558, b2 = 457.334478783897737,
+               b3 = 348.703917719495792, b4 = 170.354001821091472, b5 = 53.992906912940207,
+               b6 = 10.479857114260399;
+  const cplx zh = cmake(y, -x);
+  cplx as = cmake(a6 * zh.re + a5, a6 * zh.im);
+  as = cmul(as, zh); as.re += a4;
+  as = cmul(as, zh); as.re += a3;
+  as = cmul(as, zh); as.re += a2;
+  as = cmul(as, zh); as.re += a1;
+  as = cmul(as, zh); as.re += a0;
+  cplx bs = cmake(zh.re + b6, zh.im);
+  bs = cmul(bs, zh); bs.re += b5;
+  bs = cmul(bs, zh); bs.re += b4;
+  bs = cmul(bs, zh); bs.re += b3;
+  bs = cmul(bs, zh); bs.re += b2;
+  bs = cmul(bs, zh); bs.re += b1;
+  bs = cmul(bs, zh); bs.re += b0;
+  return cdiv_f(as, bs);
+}
 __device__ __noinline__ double sd_shape_re(double width0, double width2, double delta2, double df) {
-  return sd_shape(width0, width2, delta2, df).re;
+  const cplx cden = cmake(width2, -delta2);
+  const cplx xrt = csqrt_f(cdiv_f(cmake(width0 - 1.5 * width2, df + 1.5 * delta2), cden));
+  const cplx pxw = cscale(cmul(xrt, dcerror_f(-xrt.im, xrt.re)), kSqrtPi);
+  return cdiv_f(cmake(2.0 * (1.0 - pxw.re), -2.0 * pxw.im), cden).re;
 }
 __device__ __noinline__ double o2_sd118_sf1(double df, double d1, double y) {
   const double width2 = 0.076 * df;
-  cplx xc = cmake((df - 1.5 * width2) / width2, d1 / width2);
-  cplx xrt = csqrt_(xc);
-  cplx pxw = cscale(cmul(xrt, dcerror(-xrt.im, xrt.re)), kSqrtPi);
-  cplx one_m = cmake(2.0 * (1.0 - pxw.re), -2.0 * pxw.im);
-  cplx asd = cmul(cmake(1.0, y), one_m);
-  return asd.re / width2;
+  const double rw2 = rcp_fast(width2);
+  const cplx xrt = csqrt_f(cmake((df - 1.5 * width2) * rw2, d1 * rw2));
+  const cplx pxw = cscale(cmul(xrt, dcerror_f(-xrt.im, xrt.re)), kSqrtPi);
+  const cplx one_m = cmake(2.0 * (1.0 - pxw.re), -2.0 * pxw.im);
+  return cmul(cmake(1.0, y), one_m).re * rw2;
 }
 // Rayleigh liquid-water absorption per unit density [Np km^-1 / (g m^-3)]
 __device__ __noinline__ double liq_abs_unit(int liq_model, double f, double tk) {
@@ -80,15 +131,34 @@ __device__ __noinline__ double liq_abs_unit(int liq_model, double f, double tk) 
 }
 
 // frequency-independent state of one H2O / O2 line at one level-point
+// Fast pair form used by both species.  With u = f^2, fc = line centre, w = half width:
+//   D1 D2 = ((f-fc)^2 + w^2)((f+fc)^2 + w^2) = (u - fc^2 + w^2)^2 + 4 fc^2 w^2 = vv^2 + c4,  vv = u - c3
+//   D1 + D2 = 2 (vv + 2 fc^2),   d1 D2 - d2 D1 = 2 fc (vv - 2 w^2)
+// so a line's two wings cost per frequency: 1 DADD (vv), 1 DFMA (D), 1 DFMA (numerator = n1*vv + n0),
+// one reciprocal (MUFU.RCP64H + 3 DFMA) and 1 DFMA to accumulate: 7 FP64-pipe instructions.
+// Rounding: the only cancellation is in vv (relative error ~ eps*f/(2*max(|f-fc|, w))); lines that are
+// both narrower than 1e-3*fc and closer than 1e-3*fc to a frequency of the block take the exact
+// per-wing form in the rare-path loop instead.
 struct H2OLine {
-  double w, wsq, base, shift, sp, w2, dl2;
+  double w, wsq, base, shift, sp, w2, dl2, c3, c4, n1, n0;
 };
 struct O2Line {
-  double fcen, df, df2, as, ys, sp, y, gfac;
+  double fcen, df, df2, sp, y, gfac, c3, c4, n1, n0;
+};
+// what the hot loops keep live per line (two copies: current + prefetched next); everything else is
+// recomputed in the rare path so that 14 running sums + two of these fit in 128 registers
+struct H2OHot {
+  double c3, c4, n1, n0, b2, w, shift, w2;
+};
+struct O2Hot {
+  double c3, c4, n1, n0, df, fcen;
 };
 
 #ifndef MWRT_ABS_MINB
 #define MWRT_ABS_MINB 4
+#endif
+#ifndef MWRT_ABS_PIPELINE
+#define MWRT_ABS_PIPELINE 0   // 1: prefetch the next H2O line's state (measured slower: registers)
 #endif
 template <int FB>
 __global__ void __launch_bounds__(kAbsThreads, MWRT_ABS_MINB)
@@ -107,6 +177,9 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
   double* dfp = dfm + nh * FB;            // nh x FB: f_j + fl_i
   double* ifl2 = dfp + nh * FB;           // nh: 1/fl_i^2
   double* ifk2 = ifl2 + nh;               // no: 1/f_k^2
+  double* fsq = ifk2 + no;                // FB: f_j^2
+  double* dminh = fsq + FB;               // nh: min_j |f_j - fl_i|
+  double* dmino = dminh + nh;             // no: min_j |f_j - f_k|
   const int f0 = blockIdx.y * FB;
   for (int i = threadIdx.x; i < m.n_table; i += blockDim.x) tab[i] = m.tables[i];
   if (threadIdx.x < FB) {
@@ -122,12 +195,19 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
   for (int i = threadIdx.x; i < nh; i += blockDim.x) {
     double fl = tab[MWRT_H2O_FL * nh + i];
     ifl2[i] = 1.0 / (fl * fl);
+    double dmin = fabs(fblk[0] - fl);
+    for (int j = 1; j < FB; ++j) dmin = fmin(dmin, fabs(fblk[j] - fl));
+    dminh[i] = dmin;
   }
   const double* O = tab + MWRT_H2O_NCOL * nh;
   for (int i = threadIdx.x; i < no; i += blockDim.x) {
     double fk = O[MWRT_O2_F * no + i];
     ifk2[i] = 1.0 / (fk * fk);
+    double dmin = fabs(fblk[0] - fk);
+    for (int j = 1; j < FB; ++j) dmin = fmin(dmin, fabs(fblk[j] - fk));
+    dmino[i] = dmin;
   }
+  if (threadIdx.x < FB) fsq[threadIdx.x] = fblk[threadIdx.x] * fblk[threadIdx.x];
   __syncthreads();
 
   const long long ipt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,20 +232,20 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     if (status && in_bad) atomicOr(&status[pidx], in_nan ? MWRT_ST_NAN_INPUT : MWRT_ST_RANGE);
   }
 
-  double fmin = fblk[0], fmax = fblk[0];
+  double f_lo = fblk[0], f_hi = fblk[0];
 #pragma unroll
   for (int j = 1; j < FB; ++j) {
-    fmin = fmin < fblk[j] ? fmin : fblk[j];
-    fmax = fmax > fblk[j] ? fmax : fblk[j];
+    f_lo = f_lo < fblk[j] ? f_lo : fblk[j];
+    f_hi = f_hi > fblk[j] ? f_hi : fblk[j];
   }
 
   // level-point state, in the rounding order of RTEquation.clearsky_absorption
-  const double vx = 300.0 / tk;
-  const double ekpa = e_mb / 10.0;
-  const double pdrykpa = p_mb / 10.0 - ekpa;
-  const double t = 300.0 / vx;
+  const double vx = div_fast(300.0, tk);   // div_fast: <= 1 ulp from IEEE, no slow-path branch
+  const double ekpa = div_fast(e_mb, 10.0);
+  const double pdrykpa = div_fast(p_mb, 10.0) - ekpa;
+  const double t = div_fast(300.0, vx);
   const double pp = (pdrykpa + ekpa) * 10.0;
-  const double rho = ekpa * 10.0 / (kRvapAbs * t);
+  const double rho = div_fast(ekpa * 10.0, kRvapAbs * t);
 
   const long long obase = (pidx * F + f0) * (long long)L + lev;  // + j*L per frequency
   double acc[FB];
@@ -173,15 +253,15 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
 
   // ------------------------------------------------------------------ H2O (abh2o)
   {
-    const double pvap = (rho * t) / m.h2o_pvap_div;
+    const double pvap = div_fast(rho * t, m.h2o_pvap_div);
     const double pda = pp - pvap;
     const double den = m.h2o_den_const * rho;
-    const double tic = m.h2o_reftcon / t;
-    const double ticln = log(tic);
+    const double tic = div_fast(m.h2o_reftcon, t);
+    const double ticln = log_nb(tic);
     const double conbase =
         (m.h2o_cf * pda * exp_nb(m.h2o_xcf * ticln) + m.h2o_cs * pvap * exp_nb(m.h2o_xcs * ticln)) * pvap;
-    const double ti = m.h2o_reftline / t;
-    const double tiln = log(ti);
+    const double ti = div_fast(m.h2o_reftline, t);
+    const double tiln = log_nb(ti);
     const double omti = 1.0 - ti;
     const double* H = tab;
     const bool sd_on = m.h2o_sd != 0;
@@ -201,51 +281,71 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
       h.base = h.w * rcp_fast(562500.0 + h.wsq);
       // strength with (1/fl)^2 folded in; the common f^2 is applied once at the end
       h.sp = H[MWRT_H2O_S1 * nh + i] * exp_nb(fma(2.5, tiln, H[MWRT_H2O_B2 * nh + i] * omti)) * ifl2[i];
+      // fast pair form: sp*w*(D0+D1)/(D0 D1) = (n1*vv + n0) / (vv^2 + c4)
+      const double fc = H[MWRT_H2O_FL * nh + i] + h.shift;
+      const double fc2 = fc * fc;
+      h.c3 = fc2 - h.wsq;
+      h.c4 = 4.0 * fc2 * h.wsq;
+      h.n1 = 2.0 * (h.sp * h.w);
+      h.n0 = h.n1 * (2.0 * fc2);
       return h;
     };
 
 #pragma unroll
     for (int j = 0; j < FB; ++j) acc[j] = 0.0;
     double basesum = 0.0;
-    H2OLine nxt = hoist(0);
+    auto hot = [&](int i) {
+      const H2OLine g = hoist(i);
+      return H2OHot{g.c3, g.c4, g.n1, g.n0, 2.0 * g.sp * g.base, g.w, g.shift, g.w2};
+    };
+#if MWRT_ABS_PIPELINE
+    H2OHot nxt = hot(0);
+#endif
     for (int i = 0; i < nh; ++i) {
-      const H2OLine h = nxt;
-      nxt = hoist(i + 1 < nh ? i + 1 : i);  // next line's exp chains overlap this line's wing loop
-      const double* dm = dfm + i * FB;
-      const double* dp = dfp + i * FB;
-      // unconditional fast form, both wings inside the 750 GHz cutoff, plain Lorentz:
-      //   w/(d0^2+w^2) + w/(d1^2+w^2) = w (D0+D1) / (D0 D1)   -> one reciprocal per (line, f)
-      const double sw = h.sp * h.w;
-      basesum = fma(2.0 * h.sp, h.base, basesum);
+#if MWRT_ABS_PIPELINE
+      const H2OHot h = nxt;
+      nxt = hot(i + 1 < nh ? i + 1 : i);  // next line's exp chains overlap this line's wing loop
+#else
+      const H2OHot h = hot(i);
+#endif
+      // unconditional fast form (both wings inside the 750 GHz cutoff, plain Lorentz):
+      // 7 FP64-pipe instructions per (line, frequency), see H2OLine
+      basesum += h.b2;
 #pragma unroll
       for (int j = 0; j < FB; ++j) {
-        const double d0 = dm[j] - h.shift;
-        const double d1 = dp[j] + h.shift;
-        const double D0 = fma(d0, d0, h.wsq);
-        const double D1 = fma(d1, d1, h.wsq);
-        const double q = (D0 + D1) * rcp_fast(D0 * D1);
-        acc[j] = fma(sw, q, acc[j]);
+        const double vv = fsq[j] - h.c3;
+        const double D = fma(vv, vv, h.c4);
+        const double num = fma(h.n1, vv, h.n0);
+        acc[j] = fma(num, rcp_fast(D), acc[j]);
       }
-      // rare corrections: a wing beyond the cutoff, or the speed-dependent shape near line centre
-      const double fc = tab[MWRT_H2O_FL * nh + i] + h.shift;
-      const bool all_in = (fc + fmax < 750.0) && (fc - fmin < 750.0) && (fmax - fc < 750.0);
-      const bool sd_any = (h.w2 > 0.0) && (fmin - fc < 10.0 * h.w) && (fc - fmax < 10.0 * h.w);
-      if (!all_in || sd_any) {
+      // rare path: a wing beyond the cutoff, the speed-dependent shape near line centre, or a line
+      // that is both very narrow and very close to a frequency (exact per-wing form, oracle rounding)
+      const double fl = tab[MWRT_H2O_FL * nh + i];
+      const double fc = fl + h.shift;
+      const bool all_in = (fc + f_hi < 750.0) && (fc - f_lo < 750.0) && (f_hi - fc < 750.0);
+      const bool sd_any = (h.w2 > 0.0) && (f_lo - fc < 10.0 * h.w) && (fc - f_hi < 10.0 * h.w);
+      const bool narrow = (h.w < 1e-3 * fl) && (dminh[i] - fabs(h.shift) < 1e-3 * fl);
+      if (!all_in || sd_any || narrow) {
+        const H2OLine g = hoist(i);   // full line state, recomputed: this path is rare
+        const double* dm = dfm + i * FB;
+        const double* dp = dfp + i * FB;
 #pragma unroll 1
         for (int j = 0; j < FB; ++j) {
-          const double d0 = dm[j] - h.shift;
-          const double d1 = dp[j] + h.shift;
-          const double l0 = div_fast(h.w, fma(d0, d0, h.wsq));
-          double c = 0.0;
-          if (h.w2 > 0.0 && fabs(d0) < 10.0 * h.w)
-            c += sd_shape_re(h.w, h.w2, h.dl2, d0) - l0;   // replace Lorentz by the SD shape
-          else if (!(fabs(d0) < 750.0))
-            c -= l0 - h.base;                               // wing outside the cutoff: remove it
-          if (!(fabs(d1) < 750.0)) c -= div_fast(h.w, fma(d1, d1, h.wsq)) - h.base;
-          tmp[j] = c;
+          const double d0 = dm[j] - g.shift;
+          const double d1 = dp[j] + g.shift;
+          double ex = 0.0;   // what the oracle adds for this line: sum over wings of (shape - base)
+          if (g.w2 > 0.0 && fabs(d0) < 10.0 * g.w)
+            ex += sd_shape_re(g.w, g.w2, g.dl2, d0) - g.base;
+          else if (fabs(d0) < 750.0)
+            ex += div_fast(g.w, fma(d0, d0, g.wsq)) - g.base;
+          if (fabs(d1) < 750.0) ex += div_fast(g.w, fma(d1, d1, g.wsq)) - g.base;
+          // minus what the fast form contributed (recomputed bit-identically), base term included
+          const double vv = fsq[j] - g.c3;
+          const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
+          tmp[j] = fma(g.sp, ex + 2.0 * g.base, -fast);
         }
 #pragma unroll
-        for (int j = 0; j < FB; ++j) acc[j] = fma(h.sp, tmp[j], acc[j]);
+        for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
       }
     }
     const double lc = m.h2o_line_const * den;
@@ -261,11 +361,11 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
 
   // ------------------------------------------------------------------ O2 (o2abs) + N2
   {
-    const double th = 300.0 / t;
+    const double th = div_fast(300.0, t);
     const double th1 = th - 1.0;
-    const double thln = log(th);
+    const double thln = log_nb(th);
     const double b = exp_nb(m.o2_x * thln);
-    const double preswv = rho * t / m.o2_pvap_div;
+    const double preswv = div_fast(rho * t, m.o2_pvap_div);
     const double presda = pp - preswv;
     const double den = 0.001 * (presda * b + m.o2_h2o_broad * preswv * th);
     const double dens = 0.001 * (presda + m.o2_h2o_broad * preswv) * th;
@@ -274,53 +374,83 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     const double ymul = (m.o2_mixing == 1) ? 0.001 * pp * b : den;
     const bool dens118 = m.o2_dens118 != 0;
 
-    auto hoist = [&](int k) {
+    auto hoist = [&](int k, double expv) {   // expv = exp(-be_k * th1)
       O2Line o;
       const double wden = (dens118 && k == 0) ? dens : den;
       o.df = O[MWRT_O2_W300 * no + k] * wden;
       o.y = ymul * (O[MWRT_O2_Y0 * no + k] + O[MWRT_O2_Y1 * no + k] * th1);
       o.gfac = 1.0 + pe2 * (O[MWRT_O2_G0 * no + k] + O[MWRT_O2_G1 * no + k] * th1);
       o.fcen = O[MWRT_O2_F * no + k] + pe2 * (O[MWRT_O2_DNU0 * no + k] + O[MWRT_O2_DNU1 * no + k] * th1);
-      o.sp = O[MWRT_O2_S300 * no + k] * exp_nb(-O[MWRT_O2_BE * no + k] * th1) * ifk2[k];
+      o.sp = O[MWRT_O2_S300 * no + k] * expv * ifk2[k];
       o.df2 = o.df * o.df;
-      o.as = o.sp * (o.df * o.gfac);
-      o.ys = o.sp * o.y;
+      // fast pair form: sp*(sf1+sf2) = (n1*vv + n0)/(vv^2 + c4) with As = sp*df*g, P = sp*y*fc:
+      //   n1 = 2 (As + P),  n0 = 4 (As fc^2 - P w^2)
+      const double as = o.sp * (o.df * o.gfac);
+      const double pp_ = (o.sp * o.y) * o.fcen;
+      const double fc2 = o.fcen * o.fcen;
+      o.c3 = fc2 - o.df2;
+      o.c4 = 4.0 * fc2 * o.df2;
+      o.n1 = 2.0 * (as + pp_);
+      o.n0 = 4.0 * fma(as, fc2, -pp_ * o.df2);
       return o;
     };
 
 #pragma unroll
     for (int j = 0; j < FB; ++j) acc[j] = 0.0;
-    O2Line nxt = hoist(0);
-    for (int k = 0; k < no; ++k) {
-      const O2Line o = nxt;
-      nxt = hoist(k + 1 < no ? k + 1 : k);
-      // sf1 + sf2 = (n1 D2 + n2 D1) / (D1 D2), strength folded into the numerators
+    auto hot = [&](int k, double expv) {
+      const O2Line g = hoist(k, expv);
+      return O2Hot{g.c3, g.c4, g.n1, g.n0, g.df, g.fcen};
+    };
+    // The line strengths need one exp each: a 17-deep serial chain.  They are evaluated G at a time,
+    // interleaved (exp_nb_vec), so the FP64 pipe sees G independent chains instead of one; the
+    // values are handed to the line loop by rotating a small register array (no dynamic indexing).
+    constexpr int G = 7;
+    for (int k0 = 0; k0 < no; k0 += G) {
+      double ea[G], ev[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) ea[g] = -O[MWRT_O2_BE * no + (k0 + g < no ? k0 + g : no - 1)] * th1;
+      exp_nb_vec<G>(ea, ev);
+#pragma unroll 1
+      for (int gi = 0; gi < G; ++gi) {
+      const int k = k0 + gi;
+      if (k >= no) break;
+      const double expv = ev[0];
+#pragma unroll
+      for (int q = 0; q + 1 < G; ++q) ev[q] = ev[q + 1];
+      const O2Hot o = hot(k, expv);
+      // sp*(sf1 + sf2) in the fast pair form: 7 FP64-pipe instructions per (line, frequency)
 #pragma unroll
       for (int j = 0; j < FB; ++j) {
-        const double f = fblk[j];
-        const double d1 = f - o.fcen;
-        const double d2 = f + o.fcen;
-        const double D1 = fma(d1, d1, o.df2);
-        const double D2 = fma(d2, d2, o.df2);
-        const double n1 = fma(d1, o.ys, o.as);
-        const double n2 = fma(-d2, o.ys, o.as);
-        const double num = fma(n1, D2, n2 * D1);
-        acc[j] = fma(num, rcp_fast(D1 * D2), acc[j]);
+        const double vv = fsq[j] - o.c3;
+        const double D = fma(vv, vv, o.c4);
+        const double num = fma(o.n1, vv, o.n0);
+        acc[j] = fma(num, rcp_fast(D), acc[j]);
       }
-      if (m.o2_sd118 && k == 0 && (fmin - o.fcen < 10.0 * o.df) && (o.fcen - fmax < 10.0 * o.df)) {
-        // speed-dependent 118.75 GHz line: replace sf1 where |f - fcen| < 10 df
+      // rare path: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency
+      const double fk = O[MWRT_O2_F * no + k];
+      const bool sd = m.o2_sd118 && k == 0 && (f_lo - o.fcen < 10.0 * o.df) && (o.fcen - f_hi < 10.0 * o.df);
+      const bool narrow = (o.df < 1e-3 * fk) && (dmino[k] - fabs(o.fcen - fk) < 1e-3 * fk);
+      if (sd || narrow) {
+        const O2Line g = hoist(k, expv);   // full line state, recomputed: this path is rare
 #pragma unroll 1
         for (int j = 0; j < FB; ++j) {
-          const double d1 = fblk[j] - o.fcen;
-          double c = 0.0;
-          if (fabs(d1) < 10.0 * o.df)
-            c = o2_sd118_sf1(o.df, d1, o.y) - div_fast(o.df * o.gfac + d1 * o.y, fma(d1, d1, o.df2));
-          tmp[j] = c;
+          const double d1 = fblk[j] - g.fcen;
+          const double d2 = fblk[j] + g.fcen;
+          double sf1;
+          if (sd && fabs(d1) < 10.0 * g.df)
+            sf1 = o2_sd118_sf1(g.df, d1, g.y);
+          else
+            sf1 = div_fast(g.df * g.gfac + d1 * g.y, fma(d1, d1, g.df2));
+          const double sf2 = div_fast(g.df * g.gfac - d2 * g.y, fma(d2, d2, g.df2));
+          const double vv = fsq[j] - g.c3;
+          const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
+          tmp[j] = fma(g.sp, sf1 + sf2, -fast);
         }
 #pragma unroll
-        for (int j = 0; j < FB; ++j) acc[j] = fma(o.sp, tmp[j], acc[j]);
+        for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
       }
-    }
+      }   // lines of the group
+    }     // groups
     const double scale = m.o2_abs_const * presda * (th * th * th);
     const double pdry_mb = pdrykpa * 10.0;
     const double n2base = m.n2_n * (m.n2_l * pdry_mb * pdry_mb * exp_nb(m.n2_m * thln));
@@ -376,7 +506,7 @@ static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, c
                       double* adry, double* aliq, double* aice, int* status, cudaStream_t st) {
   const long long npts = (long long)P * L;
   dim3 grid((unsigned)((npts + kAbsThreads - 1) / kAbsThreads), (unsigned)((F + FB - 1) / FB));
-  size_t smem = sizeof(double) * (size_t)(m.n_table + FB + 2 * m.n_h2o * FB + m.n_h2o + m.n_o2);
+  size_t smem = sizeof(double) * (size_t)(m.n_table + 2 * FB + 2 * m.n_h2o * FB + 2 * (m.n_h2o + m.n_o2));
   k_absorption<FB><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, p, tk, e, e_is_rh, e_out, rho_out,
                                                     denliq, denice, frq, awet, adry, aliq, aice,
                                                     status);
