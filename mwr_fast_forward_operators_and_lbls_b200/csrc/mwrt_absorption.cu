@@ -24,6 +24,7 @@
 namespace mwrt {
 
 constexpr int kAbsThreads = 128;
+constexpr int kAllIn = 0, kAllOut = 1, kWing1Out = 2, kMixed = 3;
 
 // rare-path helpers are kept out of line: the hot loops must stay small enough for the
 // instruction caches (the first version inlined them 14x and stalled on instruction fetch)
@@ -180,6 +181,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
   double* fsq = ifk2 + no;                // FB: f_j^2
   double* dminh = fsq + FB;               // nh: min_j |f_j - fl_i|
   double* dmino = dminh + nh;             // no: min_j |f_j - f_k|
+  int* hcls = reinterpret_cast<int*>(dmino + no);   // nh: H2O line class w.r.t. the 750 GHz cutoff
   const int f0 = blockIdx.y * FB;
   for (int i = threadIdx.x; i < m.n_table; i += blockDim.x) tab[i] = m.tables[i];
   if (threadIdx.x < FB) {
@@ -195,9 +197,19 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
   for (int i = threadIdx.x; i < nh; i += blockDim.x) {
     double fl = tab[MWRT_H2O_FL * nh + i];
     ifl2[i] = 1.0 / (fl * fl);
-    double dmin = fabs(fblk[0] - fl);
-    for (int j = 1; j < FB; ++j) dmin = fmin(dmin, fabs(fblk[j] - fl));
+    double dmin = fabs(fblk[0] - fl), lo = fblk[0], hi = fblk[0];
+    for (int j = 1; j < FB; ++j) {
+      dmin = fmin(dmin, fabs(fblk[j] - fl));
+      lo = fmin(lo, fblk[j]);
+      hi = fmax(hi, fblk[j]);
+    }
     dminh[i] = dmin;
+    const bool w0_in = (fl - lo < 749.0) && (hi - fl < 749.0);   // |f - fc| < 750 for every f
+    int cls = kMixed;
+    if (w0_in && fl + hi < 749.0) cls = kAllIn;
+    else if (w0_in && fl + lo > 751.0) cls = kWing1Out;
+    else if (fl - hi > 751.0 || lo - fl > 751.0) cls = kAllOut;
+    hcls[i] = cls;
   }
   const double* O = tab + MWRT_H2O_NCOL * nh;
   for (int i = threadIdx.x; i < no; i += blockDim.x) {
@@ -270,10 +282,12 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
       H2OLine h;
       h.w = H[MWRT_H2O_W0 * nh + i] * pda * exp_nb(H[MWRT_H2O_X * nh + i] * tiln) +
             H[MWRT_H2O_W0S * nh + i] * pvap * exp_nb(H[MWRT_H2O_XS * nh + i] * tiln);
-      const double shf = H[MWRT_H2O_SH * nh + i] * pda * (1.0 - H[MWRT_H2O_AAIR * nh + i] * tiln) *
-                         exp_nb(H[MWRT_H2O_XH * nh + i] * tiln);
-      const double shs = H[MWRT_H2O_SHS * nh + i] * pvap * (1.0 - H[MWRT_H2O_ASELF * nh + i] * tiln) *
-                         exp_nb(H[MWRT_H2O_XHS * nh + i] * tiln);
+      // ti^0 = 1 exactly: most lines have no shift exponent, skip their exp (warp-uniform branch)
+      double shf = H[MWRT_H2O_SH * nh + i] * pda * (1.0 - H[MWRT_H2O_AAIR * nh + i] * tiln);
+      double shs = H[MWRT_H2O_SHS * nh + i] * pvap * (1.0 - H[MWRT_H2O_ASELF * nh + i] * tiln);
+      const double xh = H[MWRT_H2O_XH * nh + i], xhs = H[MWRT_H2O_XHS * nh + i];
+      if (xh != 0.0) shf *= exp_nb(xh * tiln);
+      if (xhs != 0.0) shs *= exp_nb(xhs * tiln);
       h.shift = H[MWRT_H2O_SR * nh + i] * h.w + shf + shs;
       h.w2 = sd_on ? H[MWRT_H2O_W2 * nh + i] * pda + H[MWRT_H2O_W2S * nh + i] * pvap : 0.0;
       h.dl2 = sd_on ? H[MWRT_H2O_D2 * nh + i] * pda + H[MWRT_H2O_D2S * nh + i] * pvap : 0.0;
@@ -298,51 +312,86 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
       const H2OLine g = hoist(i);
       return H2OHot{g.c3, g.c4, g.n1, g.n0, 2.0 * g.sp * g.base, g.w, g.shift, g.w2};
     };
-#if MWRT_ABS_PIPELINE
-    H2OHot nxt = hot(0);
-#endif
+    // Per-CTA line classes w.r.t. the 750 GHz cutoff (uniform branches, decided from the table
+    // centre with a 1 GHz margin for the pressure shift):
+    //   kAllIn    both wings of every block frequency inside  -> fast pair form
+    //   kAllOut   both wings outside (e.g. 916 GHz below 166 GHz) -> contributes exactly 0: skipped
+    //   kWing1Out f+fc always outside, f-fc always inside (e.g. 752 GHz) -> one Lorentzian per frequency
+    //   kMixed    anything else -> exact per-wing loop
     for (int i = 0; i < nh; ++i) {
-#if MWRT_ABS_PIPELINE
-      const H2OHot h = nxt;
-      nxt = hot(i + 1 < nh ? i + 1 : i);  // next line's exp chains overlap this line's wing loop
-#else
+      const int cls = hcls[i];
+      if (cls == kAllOut) continue;
       const H2OHot h = hot(i);
-#endif
-      // unconditional fast form (both wings inside the 750 GHz cutoff, plain Lorentz):
-      // 7 FP64-pipe instructions per (line, frequency), see H2OLine
-      basesum += h.b2;
-#pragma unroll
-      for (int j = 0; j < FB; ++j) {
-        const double vv = fsq[j] - h.c3;
-        const double D = fma(vv, vv, h.c4);
-        const double num = fma(h.n1, vv, h.n0);
-        acc[j] = fma(num, rcp_fast(D), acc[j]);
-      }
-      // rare path: a wing beyond the cutoff, the speed-dependent shape near line centre, or a line
-      // that is both very narrow and very close to a frequency (exact per-wing form, oracle rounding)
       const double fl = tab[MWRT_H2O_FL * nh + i];
       const double fc = fl + h.shift;
-      const bool all_in = (fc + f_hi < 750.0) && (fc - f_lo < 750.0) && (f_hi - fc < 750.0);
-      const bool sd_any = (h.w2 > 0.0) && (f_lo - fc < 10.0 * h.w) && (fc - f_hi < 10.0 * h.w);
-      const bool narrow = (h.w < 1e-3 * fl) && (dminh[i] - fabs(h.shift) < 1e-3 * fl);
-      if (!all_in || sd_any || narrow) {
-        const H2OLine g = hoist(i);   // full line state, recomputed: this path is rare
+      const bool margin_ok = fabs(h.shift) < 1.0;
+      if (cls == kAllIn && margin_ok) {
+        // 7 FP64-pipe instructions per (line, frequency), see H2OLine
+        basesum += h.b2;
+#pragma unroll
+        for (int j = 0; j < FB; ++j) {
+          const double vv = fsq[j] - h.c3;
+          const double D = fma(vv, vv, h.c4);
+          const double num = fma(h.n1, vv, h.n0);
+          acc[j] = fma(num, rcp_fast(D), acc[j]);
+        }
+        // corrections: the speed-dependent shape near line centre, or a line that is both very
+        // narrow and very close to a frequency (exact per-wing form in the oracle's rounding order)
+        const bool sd_any = (h.w2 > 0.0) && (f_lo - fc < 10.0 * h.w) && (fc - f_hi < 10.0 * h.w);
+        const bool narrow = (h.w < 1e-3 * fl) && (dminh[i] - fabs(h.shift) < 1e-3 * fl);
+        if (sd_any || narrow) {
+          const H2OLine g = hoist(i);   // full line state, recomputed
+          const double* dm = dfm + i * FB;
+          const double* dp = dfp + i * FB;
+#pragma unroll 1
+          for (int j = 0; j < FB; ++j) {
+            const double d0 = dm[j] - g.shift;
+            const double d1 = dp[j] + g.shift;
+            const bool use_sd = g.w2 > 0.0 && fabs(d0) < 10.0 * g.w;
+            if (!use_sd && !narrow) {   // this frequency keeps the fast form: no correction
+              tmp[j] = 0.0;
+              continue;
+            }
+            double ex;   // what the oracle adds for this line: sum over wings of (shape - base)
+            if (use_sd)
+              ex = sd_shape_re(g.w, g.w2, g.dl2, d0) - g.base;
+            else
+              ex = div_fast(g.w, fma(d0, d0, g.wsq)) - g.base;
+            ex += div_fast(g.w, fma(d1, d1, g.wsq)) - g.base;
+            // minus what the fast form contributed (recomputed bit-identically), base term included
+            const double vv = fsq[j] - g.c3;
+            const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
+            tmp[j] = fma(g.sp, ex + 2.0 * g.base, -fast);
+          }
+#pragma unroll
+          for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
+        }
+      } else if (cls == kWing1Out && margin_ok && !(h.w2 > 0.0)) {
+        // only the f - fc wing is inside the cutoff: sp * (w / (d0^2 + w^2) - base)
+        basesum += 0.5 * h.b2;
+        const double sw = 0.5 * h.n1, wsq = h.w * h.w;
+        const double* dm = dfm + i * FB;
+#pragma unroll
+        for (int j = 0; j < FB; ++j) {
+          const double d0 = dm[j] - h.shift;
+          acc[j] = fma(sw, rcp_fast(fma(d0, d0, wsq)), acc[j]);
+        }
+      } else {
+        // exact per-wing evaluation with the cutoff tests (rare: a line within ~1 GHz of f +- 750)
+        const H2OLine g = hoist(i);
         const double* dm = dfm + i * FB;
         const double* dp = dfp + i * FB;
 #pragma unroll 1
         for (int j = 0; j < FB; ++j) {
           const double d0 = dm[j] - g.shift;
           const double d1 = dp[j] + g.shift;
-          double ex = 0.0;   // what the oracle adds for this line: sum over wings of (shape - base)
+          double ex = 0.0;
           if (g.w2 > 0.0 && fabs(d0) < 10.0 * g.w)
             ex += sd_shape_re(g.w, g.w2, g.dl2, d0) - g.base;
           else if (fabs(d0) < 750.0)
             ex += div_fast(g.w, fma(d0, d0, g.wsq)) - g.base;
           if (fabs(d1) < 750.0) ex += div_fast(g.w, fma(d1, d1, g.wsq)) - g.base;
-          // minus what the fast form contributed (recomputed bit-identically), base term included
-          const double vv = fsq[j] - g.c3;
-          const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
-          tmp[j] = fma(g.sp, ex + 2.0 * g.base, -fast);
+          tmp[j] = g.sp * ex;
         }
 #pragma unroll
         for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
@@ -506,7 +555,7 @@ static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, c
                       double* adry, double* aliq, double* aice, int* status, cudaStream_t st) {
   const long long npts = (long long)P * L;
   dim3 grid((unsigned)((npts + kAbsThreads - 1) / kAbsThreads), (unsigned)((F + FB - 1) / FB));
-  size_t smem = sizeof(double) * (size_t)(m.n_table + 2 * FB + 2 * m.n_h2o * FB + 2 * (m.n_h2o + m.n_o2));
+  size_t smem = sizeof(double) * (size_t)(m.n_table + 2 * FB + 2 * m.n_h2o * FB + 2 * (m.n_h2o + m.n_o2) + (m.n_h2o + 1) / 2 + 1);
   k_absorption<FB><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, p, tk, e, e_is_rh, e_out, rho_out,
                                                     denliq, denice, frq, awet, adry, aliq, aice,
                                                     status);
