@@ -45,6 +45,13 @@ __device__ __forceinline__ double bright(double hvk, double b) {
   if (b > 0.0 || isnan(b)) return hvk / log(1.0 + 1.0 / b);
   return 0.0;
 }
+// bright() without library calls or branches: b <= 0 -> 0, NaN -> NaN, else hvk / log(1 + 1/b)
+__device__ __forceinline__ double bright_nb(double hvk, double b) {
+  const bool pos = b > 0.0;
+  const double x = 1.0 + rcp_fast(pos ? b : 1.0);
+  const double t = hvk * rcp_fast(log_nb(x));
+  return pos ? t : (isnan(b) ? b : 0.0);
+}
 
 // PLANE = plane-parallel path: ds(a, layer) = dz(layer) * amass(a) is formed in registers from z and
 // a per-angle air-mass table (no ds array, no slant-path kernel); otherwise ds is read from (P,A,L).
@@ -209,20 +216,20 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
   for (int a = 0; a < NA; ++a) {
     if (a0 + a >= A) break;
     const double tp = PLANE ? tauprof[0] * amass[a] : tauprof[a];
-    double boftotl, boftmr;
-    if (tp < kExpMax) {
-      const double et = exp(-tp);
-      boftotl = bbg * et + batm[a];
-      boftmr = batm[a] / (1.0 - et);
-    } else {
-      boftotl = batm[a];
-      boftmr = batm[a];
-    }
-    double o_tot = bright(hvk, boftotl), o_atm = bright(hvk, batm[a]), o_mr = bright(hvk, boftmr);
+    // cosmic background / T_mr (RTEquation.planck) and the inverse Planck function (bright), with the
+    // branch-free exp/log/reciprocal helpers: NA angles x 3 outputs would otherwise inline ~6000
+    // instructions of library slow paths here
+    const bool thin = tp < kExpMax;
+    const double et = exp_nb(fmax(-tp, -700.0));
+    const double boftotl = thin ? fma(bbg, et, batm[a]) : batm[a];
+    const double boftmr = thin ? batm[a] * rcp_fast(1.0 - et) : batm[a];
+    const double o_tot = bright_nb(hvk, boftotl), o_atm0 = bright_nb(hvk, batm[a]);
+    const double o_mr0 = bright_nb(hvk, boftmr);
+    double o_tot_ = o_tot, o_atm = o_atm0, o_mr = o_mr0;
     double o_w = PLANE ? sw[0] * amass[a] : sw[a], o_d = PLANE ? sd[0] * amass[a] : sd[a];
     double o_l = PLANE ? sl[0] * amass[a] : sl[a], o_i = PLANE ? si[0] * amass[a] : si[a];
-    if (bad) o_tot = o_atm = o_mr = o_w = o_d = o_l = o_i = nan("");
-    if (tbtotal) tbtotal[obase + a] = o_tot;
+    if (bad) o_tot_ = o_atm = o_mr = o_w = o_d = o_l = o_i = nan("");
+    if (tbtotal) tbtotal[obase + a] = o_tot_;
     if (tbatm) tbatm[obase + a] = o_atm;
     if (tmr) tmr[obase + a] = o_mr;
     if (tauwet) tauwet[obase + a] = o_w;
