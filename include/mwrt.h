@@ -149,6 +149,11 @@ int mwrt_plan_create(const mwrt_model* m, int L, int F, int A, const double* frq
                      int flags, int chunk_profiles, mwrt_plan** out);
 int mwrt_plan_destroy(mwrt_plan* plan);
 int mwrt_plan_set_emissivity(mwrt_plan* plan, double es);
+/* pieces > 1: mwrt_plan_forward_device cuts the batch into `pieces` parts and overlaps kernel 3 of
+ * part c (on a stream owned by the plan) with kernel 1 of part c+1 (on the caller's stream); the
+ * caller's stream still completes after everything.  The host entry point uses 2*pieces chunks.
+ * Default 1 (no split). */
+int mwrt_plan_set_split(mwrt_plan* plan, int pieces);
 /* optional band-pass: C channels x S sub-frequencies (C*S == F), host weights (C,S) or NULL = 1/S.
  * Outputs of the forward calls become (P,C,A). */
 int mwrt_plan_set_bandpass(mwrt_plan* plan, int C, int S, const double* weights);

@@ -69,10 +69,16 @@ struct mwrt_plan {
   double* d_angles;
   double* d_amass;   // (A,) 1/sin(elevation), computed on the host like PyRTlib does
   double* d_bpw;     // (C,S) weights or null (uniform)
-  // workspace for `cap` profiles
-  int cap;
-  double *w_awet, *w_adry, *w_aliq, *w_aice, *w_ds, *w_e;
-  double* w_mono[7];  // monochromatic RTE outputs when band-pass is on
+  // workspace for `cap` profiles, in `nslots` (1 or 2) independent slots: with two slots kernel 3 of
+  // chunk c runs on `s_aux` while kernel 1 of chunk c+1 runs on the caller's stream
+  int cap, nslots, split;
+  struct Slot {
+    double *awet, *adry, *aliq, *aice, *ds, *e;
+    double* mono[7];  // monochromatic RTE outputs when band-pass is on
+    cudaEvent_t ev_abs, ev_rte;
+    bool used;
+  } ws[2];
+  cudaStream_t s_aux;
   // host-path resources (lazily created)
   bool host_ready;
   cudaStream_t s_h2d, s_comp, s_d2h;
@@ -216,30 +222,41 @@ int mwrt_bandpass_f64(int P, int C, int S, int A, const double* in, const double
 
 // ------------------------------------------------------------------------------------ plan
 static void plan_free_ws(mwrt_plan* pl) {
-  cudaFree(pl->w_awet); cudaFree(pl->w_adry); cudaFree(pl->w_aliq); cudaFree(pl->w_aice);
-  cudaFree(pl->w_ds); cudaFree(pl->w_e);
-  for (int i = 0; i < 7; ++i) cudaFree(pl->w_mono[i]);
-  pl->w_awet = pl->w_adry = pl->w_aliq = pl->w_aice = pl->w_ds = pl->w_e = nullptr;
-  for (int i = 0; i < 7; ++i) pl->w_mono[i] = nullptr;
+  for (int k = 0; k < 2; ++k) {
+    mwrt_plan::Slot& w = pl->ws[k];
+    cudaFree(w.awet); cudaFree(w.adry); cudaFree(w.aliq); cudaFree(w.aice); cudaFree(w.ds); cudaFree(w.e);
+    for (int i = 0; i < 7; ++i) cudaFree(w.mono[i]);
+    w.awet = w.adry = w.aliq = w.aice = w.ds = w.e = nullptr;
+    for (int i = 0; i < 7; ++i) w.mono[i] = nullptr;
+    w.used = false;
+  }
   pl->cap = 0;
+  pl->nslots = 0;
 }
 
-static int plan_reserve(mwrt_plan* pl, int cap) {
-  if (cap <= pl->cap) return 0;
+static int plan_reserve(mwrt_plan* pl, int cap, int nslots) {
+  if (cap <= pl->cap && nslots <= pl->nslots) return 0;
+  cap = std::max(cap, pl->cap);
+  nslots = std::max(nslots, pl->nslots);
   plan_free_ws(pl);
   const size_t pfl = sizeof(double) * (size_t)cap * pl->F * pl->L;
-  MWRT_CUDA_OK(cudaMalloc(&pl->w_awet, pfl));
-  MWRT_CUDA_OK(cudaMalloc(&pl->w_adry, pfl));
-  if (pl->flags & MWRT_F_CLOUDY) {
-    MWRT_CUDA_OK(cudaMalloc(&pl->w_aliq, pfl));
-    MWRT_CUDA_OK(cudaMalloc(&pl->w_aice, pfl));
+  for (int k = 0; k < nslots; ++k) {
+    mwrt_plan::Slot& w = pl->ws[k];
+    MWRT_CUDA_OK(cudaMalloc(&w.awet, pfl));
+    MWRT_CUDA_OK(cudaMalloc(&w.adry, pfl));
+    if (pl->flags & MWRT_F_CLOUDY) {
+      MWRT_CUDA_OK(cudaMalloc(&w.aliq, pfl));
+      MWRT_CUDA_OK(cudaMalloc(&w.aice, pfl));
+    }
+    if (pl->flags & MWRT_F_RAY_TRACING)
+      MWRT_CUDA_OK(cudaMalloc(&w.ds, sizeof(double) * (size_t)cap * pl->A * pl->L));
+    MWRT_CUDA_OK(cudaMalloc(&w.e, sizeof(double) * (size_t)cap * pl->L));
+    if (pl->C > 0)
+      for (int i = 0; i < 7; ++i)
+        MWRT_CUDA_OK(cudaMalloc(&w.mono[i], sizeof(double) * (size_t)cap * pl->F * pl->A));
   }
-  MWRT_CUDA_OK(cudaMalloc(&pl->w_ds, sizeof(double) * (size_t)cap * pl->A * pl->L));
-  MWRT_CUDA_OK(cudaMalloc(&pl->w_e, sizeof(double) * (size_t)cap * pl->L));
-  if (pl->C > 0)
-    for (int i = 0; i < 7; ++i)
-      MWRT_CUDA_OK(cudaMalloc(&pl->w_mono[i], sizeof(double) * (size_t)cap * pl->F * pl->A));
   pl->cap = cap;
+  pl->nslots = nslots;
   return 0;
 }
 
@@ -263,7 +280,13 @@ int mwrt_plan_create(const mwrt_model* m, int L, int F, int A, const double* frq
   pl->L = L; pl->F = F; pl->A = A; pl->flags = flags;
   pl->chunk = chunk_profiles > 0 ? chunk_profiles : default_chunk(L, F, flags);
   pl->emis = 1.0;
-  cudaError_t e = cudaMalloc(&pl->d_frq, sizeof(double) * F);
+  pl->split = 1;
+  cudaError_t e = cudaStreamCreateWithFlags(&pl->s_aux, cudaStreamNonBlocking);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    e = cudaEventCreateWithFlags(&pl->ws[k].ev_abs, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ws[k].ev_rte, cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&pl->d_frq, sizeof(double) * F);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_angles, sizeof(double) * A);
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_frq, frq, sizeof(double) * F, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_angles, angles, sizeof(double) * A, cudaMemcpyHostToDevice);
@@ -298,6 +321,11 @@ int mwrt_plan_destroy(mwrt_plan* pl) {
   if (!pl) return 0;
   plan_free_host(pl);
   plan_free_ws(pl);
+  for (int k = 0; k < 2; ++k) {
+    if (pl->ws[k].ev_abs) cudaEventDestroy(pl->ws[k].ev_abs);
+    if (pl->ws[k].ev_rte) cudaEventDestroy(pl->ws[k].ev_rte);
+  }
+  if (pl->s_aux) cudaStreamDestroy(pl->s_aux);
   cudaFree(pl->d_frq); cudaFree(pl->d_angles); cudaFree(pl->d_amass); cudaFree(pl->d_bpw);
   delete pl;
   return 0;
@@ -306,6 +334,12 @@ int mwrt_plan_destroy(mwrt_plan* pl) {
 int mwrt_plan_set_emissivity(mwrt_plan* pl, double es) {
   if (!pl) return fail_arg(MWRT_E_ARG, "mwrt_plan_set_emissivity: null plan");
   pl->emis = es;
+  return 0;
+}
+
+int mwrt_plan_set_split(mwrt_plan* pl, int pieces) {
+  if (!pl || pieces < 1 || pieces > 64) return fail_arg(MWRT_E_ARG, "mwrt_plan_set_split: bad argument");
+  pl->split = pieces;
   return 0;
 }
 
@@ -327,45 +361,60 @@ int mwrt_plan_set_bandpass(mwrt_plan* pl, int C, int S, const double* weights) {
 
 int mwrt_plan_launch_count(const mwrt_plan* pl, int P) {
   if (!pl || P <= 0) return 0;
-  const int nchunk = (P + pl->chunk - 1) / pl->chunk;
+  int chunk = std::min(P, pl->chunk);
+  if (pl->split > 1 && P >= 1024 * pl->split) chunk = std::min(chunk, (P + pl->split - 1) / pl->split);
+  const int nchunk = (P + chunk - 1) / chunk;
   return nchunk * (2 + ((pl->flags & MWRT_F_RAY_TRACING) ? 1 : 0) + (pl->C > 0 ? 7 : 0));
 }
 
-// one chunk: device pointers already offset to the chunk's first profile
-static int forward_chunk(mwrt_plan* pl, int P, const mwrt_profiles& in, const mwrt_outputs& out,
-                         cudaStream_t st) {
+// one chunk: device pointers already offset to the chunk's first profile.  Kernel 1 (+2) go to
+// st_abs, kernel 3 (+ band-pass) to st_rte; when the two differ the hand-off and the reuse of the
+// workspace slot are ordered with the slot's events.
+static int forward_chunk(mwrt_plan* pl, int slot, int P, const mwrt_profiles& in,
+                         const mwrt_outputs& out, cudaStream_t st_abs, cudaStream_t st_rte) {
   const bool cloudy = pl->flags & MWRT_F_CLOUDY;
   const bool rt = pl->flags & MWRT_F_RAY_TRACING;
+  const bool two = st_abs != st_rte;
   const int L = pl->L, F = pl->F, A = pl->A;
-  if (out.status) MWRT_CUDA_OK(cudaMemsetAsync(out.status, 0, sizeof(int) * (size_t)P, st));
+  mwrt_plan::Slot& w = pl->ws[slot];
+  if (two && w.used) MWRT_CUDA_OK(cudaStreamWaitEvent(st_abs, w.ev_rte, 0));  // slot still being read?
+  if (out.status) MWRT_CUDA_OK(cudaMemsetAsync(out.status, 0, sizeof(int) * (size_t)P, st_abs));
   // kernel 1: vapour pressure + absorption (e is kept for the refractivity of kernel 2)
-  int rc = absorption_launch(pl->model, P, L, F, in.p, in.tk, in.rh, /*e_is_rh=*/1, pl->w_e, nullptr,
+  int rc = absorption_launch(pl->model, P, L, F, in.p, in.tk, in.rh, /*e_is_rh=*/1, w.e, nullptr,
                              cloudy ? in.denliq : nullptr, cloudy ? in.denice : nullptr, pl->d_frq,
-                             pl->w_awet, pl->w_adry, cloudy ? pl->w_aliq : nullptr,
-                             cloudy ? pl->w_aice : nullptr, out.status, st);
+                             w.awet, w.adry, cloudy ? w.aliq : nullptr, cloudy ? w.aice : nullptr,
+                             out.status, st_abs);
   if (rc) return rc;
   // kernel 2: refractive slant path (the plane-parallel default needs no kernel: kernel 3 forms
   // ds = dz / sin(elev) in registers)
   if (rt) {
-    rc = slant_path_launch(P, L, A, in.z, in.p, in.tk, pl->w_e, pl->d_angles, 1, pl->w_ds, out.status, st);
+    rc = slant_path_launch(P, L, A, in.z, in.p, in.tk, w.e, pl->d_angles, 1, w.ds, out.status, st_abs);
     if (rc) return rc;
+  }
+  if (two) {
+    MWRT_CUDA_OK(cudaEventRecord(w.ev_abs, st_abs));
+    MWRT_CUDA_OK(cudaStreamWaitEvent(st_rte, w.ev_abs, 0));
   }
   // kernel 3: RTE (+ band-pass epilogue)
   double* tl = (pl->flags & MWRT_F_TAU_LAYERS) ? out.tau_layer : nullptr;
   double* dst[7] = {out.tbtotal, out.tbatm, out.tmr, out.tauwet, out.taudry, out.tauliq, out.tauice};
   double* mono[7];
-  for (int i = 0; i < 7; ++i) mono[i] = (pl->C > 0) ? (dst[i] ? pl->w_mono[i] : nullptr) : dst[i];
-  rc = rte_launch(P, L, F, A, in.tk, pl->w_awet, pl->w_adry, cloudy ? pl->w_aliq : nullptr,
-                  cloudy ? pl->w_aice : nullptr, rt ? pl->w_ds : nullptr, in.z, pl->d_amass, pl->d_frq,
+  for (int i = 0; i < 7; ++i) mono[i] = (pl->C > 0) ? (dst[i] ? w.mono[i] : nullptr) : dst[i];
+  rc = rte_launch(P, L, F, A, in.tk, w.awet, w.adry, cloudy ? w.aliq : nullptr,
+                  cloudy ? w.aice : nullptr, rt ? w.ds : nullptr, in.z, pl->d_amass, pl->d_frq,
                   (pl->flags & MWRT_F_FROM_SAT) ? 1 : 0, pl->emis, mono[0], mono[1], mono[2], mono[3],
-                  mono[4], mono[5], mono[6], tl, 0, out.status, st);
+                  mono[4], mono[5], mono[6], tl, 0, out.status, st_rte);
   if (rc) return rc;
   if (pl->C > 0)
     for (int i = 0; i < 7; ++i)
       if (dst[i]) {
-        rc = bandpass_launch(P, pl->C, pl->S, A, mono[i], pl->d_bpw, dst[i], st);
+        rc = bandpass_launch(P, pl->C, pl->S, A, mono[i], pl->d_bpw, dst[i], st_rte);
         if (rc) return rc;
       }
+  if (two) {
+    MWRT_CUDA_OK(cudaEventRecord(w.ev_rte, st_rte));
+    w.used = true;
+  }
   return 0;
 }
 
@@ -401,16 +450,26 @@ int mwrt_plan_forward_device(mwrt_plan* pl, int P, const mwrt_profiles* in, cons
                              void* stream) {
   int rc = check_io(pl, P, in, out, "mwrt_plan_forward_device: bad argument");
   if (rc) return rc;
-  const int chunk = std::min(P, pl->chunk);
-  rc = plan_reserve(pl, chunk);
+  cudaStream_t st = (cudaStream_t)stream;
+  // split > 1: cut the batch into pieces and run kernel 3 of piece c on the plan's side stream while
+  // kernel 1 of piece c+1 runs on the caller's stream (two workspace slots)
+  int chunk = std::min(P, pl->chunk);
+  const bool two = pl->split > 1 && P >= 1024 * pl->split;
+  if (two) chunk = std::min(chunk, (P + pl->split - 1) / pl->split);
+  rc = plan_reserve(pl, chunk, two ? 2 : 1);
   if (rc) return rc;
   const int Fo = pl->C > 0 ? pl->C : pl->F;
-  for (int p0 = 0; p0 < P; p0 += chunk) {
+  int c = 0;
+  for (int p0 = 0; p0 < P; p0 += chunk, ++c) {
     const int n = std::min(chunk, P - p0);
-    rc = forward_chunk(pl, n, offset_in(*in, (size_t)p0 * pl->L),
-                       offset_out(*out, (size_t)p0 * Fo * pl->A, (size_t)p0 * pl->F * pl->L, p0),
-                       (cudaStream_t)stream);
+    rc = forward_chunk(pl, two ? (c & 1) : 0, n, offset_in(*in, (size_t)p0 * pl->L),
+                       offset_out(*out, (size_t)p0 * Fo * pl->A, (size_t)p0 * pl->F * pl->L, p0), st,
+                       two ? pl->s_aux : st);
     if (rc) return rc;
+  }
+  if (two) {  // the caller's stream completes only when the last kernel 3 has
+    for (int k = 0; k < 2; ++k)
+      if (pl->ws[k].used) MWRT_CUDA_OK(cudaStreamWaitEvent(st, pl->ws[k].ev_rte, 0));
   }
   return 0;
 }
@@ -444,9 +503,10 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
   int rc = check_io(pl, P, in, out, "mwrt_plan_forward_host: bad argument");
   if (rc) return rc;
   // >= 4 chunks when the batch is large enough, so copies hide behind kernels
-  int chunk = std::min(pl->chunk, std::max((P + 3) / 4, 2048));
+  const int pieces = pl->split > 1 ? 2 * pl->split : 4;
+  int chunk = std::min(pl->chunk, std::max((P + pieces - 1) / pieces, 1024));
   chunk = std::min(chunk, P);
-  rc = plan_reserve(pl, chunk);
+  rc = plan_reserve(pl, chunk, 2);
   if (rc) return rc;
   rc = plan_host_init(pl, chunk);
   if (rc) return rc;
@@ -455,9 +515,24 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
   const bool cloudy = pl->flags & MWRT_F_CLOUDY;
   const double* hin[6] = {in->z, in->p, in->tk, in->rh, in->denliq, in->denice};
   double* hout[7] = {out->tbtotal, out->tbatm, out->tmr, out->tauwet, out->taudry, out->tauliq, out->tauice};
-  int c = 0;
-  for (int p0 = 0; p0 < P; p0 += chunk, ++c) {
-    const int n = std::min(chunk, P - p0);
+  // tapered schedule: half-size first and last chunks shorten the pipeline's fill (nothing to
+  // overlap the first kernels with) and drain (nothing overlaps the last D2H copy)
+  std::vector<int> sizes;
+  if (P >= 4 * chunk - 3 && chunk >= 2048) {
+    const int half = chunk / 2;
+    int left = P - 2 * half;
+    sizes.push_back(half);
+    while (left > 0) {
+      sizes.push_back(std::min(chunk, left));
+      left -= sizes.back();
+    }
+    sizes.push_back(half);
+  } else {
+    for (int left = P; left > 0; left -= sizes.back()) sizes.push_back(std::min(chunk, left));
+  }
+  int p0 = 0;
+  for (int c = 0; c < (int)sizes.size(); p0 += sizes[c], ++c) {
+    const int n = sizes[c];
     const int s = c & 1;
     // input slot s is free once the kernels of chunk c-2 have run
     if (c >= 2) MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_h2d, pl->ev_comp[s], 0));
@@ -467,7 +542,10 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
     MWRT_CUDA_OK(cudaEventRecord(pl->ev_h2d[s], pl->s_h2d));
     MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_comp, pl->ev_h2d[s], 0));
     // output slot s is free once chunk c-2 has been copied back
-    if (c >= 2) MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_comp, pl->ev_d2h[s], 0));
+    if (c >= 2) {
+      MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_comp, pl->ev_d2h[s], 0));
+      MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_aux, pl->ev_d2h[s], 0));
+    }
     mwrt_profiles din = {pl->h_in[s][0], pl->h_in[s][1], pl->h_in[s][2], pl->h_in[s][3],
                          cloudy ? pl->h_in[s][4] : nullptr, cloudy ? pl->h_in[s][5] : nullptr};
     mwrt_outputs dout;
@@ -475,9 +553,9 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
     for (int i = 0; i < 7; ++i) *df[i] = hout[i] ? pl->h_out[s][i] : nullptr;
     dout.tau_layer = out->tau_layer ? pl->h_tl[s] : nullptr;
     dout.status = pl->h_status[s];
-    rc = forward_chunk(pl, n, din, dout, pl->s_comp);
+    rc = forward_chunk(pl, s, n, din, dout, pl->s_comp, pl->s_aux);   // kernel 3 on the side stream
     if (rc) return rc;
-    MWRT_CUDA_OK(cudaEventRecord(pl->ev_comp[s], pl->s_comp));
+    MWRT_CUDA_OK(cudaEventRecord(pl->ev_comp[s], pl->s_aux));
     MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_d2h, pl->ev_comp[s], 0));
     for (int i = 0; i < 7; ++i)
       if (hout[i])
@@ -492,6 +570,7 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
     MWRT_CUDA_OK(cudaEventRecord(pl->ev_d2h[s], pl->s_d2h));
   }
   MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_d2h));
+  MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_aux));
   MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_comp));
   return 0;
 }

@@ -89,6 +89,10 @@ class Plan:
             except Exception:
                 pass
 
+    def set_split(self, pieces):
+        """Overlap kernel 3 of one part of the batch with kernel 1 of the next (mwrt_plan_set_split)."""
+        _lib.check(self.lib.mwrt_plan_set_split(self._h, int(pieces)), "set_split")
+
     def launch_count(self, P):
         return int(self.lib.mwrt_plan_launch_count(self._h, int(P)))
 
