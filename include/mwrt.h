@@ -183,6 +183,27 @@ int mwrt_plan_forward_host(mwrt_plan* plan, int P, const mwrt_profiles* in, cons
 int mwrt_stats_f64(int T, int64_t M, const double* values, const double* refs, double* bias,
                    double* std, double* rmse, double* n_valid, void* stream);
 
+/* ---- next to the path: profile pre-processing core, batched over S sondes ----
+ * /root/reference/python_src/preproc/preprocessing4all.py.  All pointers device memory.
+ * mwrt_thin_mean_f64: running_mean_from_arrays (:156-169) over the thinning pattern (:282-285).
+ *   raw h,t,p,rh: (S,N) sonde samples; inds: (S,M) int32 thinning indices, n_inds: (S,) valid counts
+ *   (M <= 256); z_offset: (S,) metres subtracted from the thinned heights, or NULL.
+ *   Out (S,M): thinned z, and segment nan-means of t, p, rh (first/last point: the sample itself). */
+int mwrt_thin_mean_f64(int S, int N, int M, const double* h, const double* t, const double* p,
+                       const double* rh, const int32_t* inds, const int32_t* n_inds,
+                       const double* z_offset, double* z_out, double* t_out, double* p_out,
+                       double* rh_out, void* stream);
+/* mwrt_assemble_levels_f64: RH scaling and humidity conversions (:104-130, :302-312), z/p jump
+ *   rejection (:315-331), climatology top-up above the sonde's pressure threshold (add_clim2profiles
+ *   :478-531; climatology levels cz_km,cp,ct,cgkg,crh: (K,) ground-first, K <= 64), lowest2tenhPa
+ *   (:450-474), flip to top-first and selection of the lowest n_levels (:807-814).
+ *   Out (S,n_levels) top-first: p [hPa], t [K], ppmv, h2o [g/kg], z [m], rh [%]; ok (S,) 0 = rejected. */
+int mwrt_assemble_levels_f64(int S, int M, int K, int n_levels, double min_p, const double* z,
+                             const double* t, const double* p, const double* rh, const int32_t* n_inds,
+                             const double* cz_km, const double* cp, const double* ct, const double* cgkg,
+                             const double* crh, double* o_p, double* o_t, double* o_ppmv, double* o_h2o,
+                             double* o_z, double* o_rh, int32_t* ok, void* stream);
+
 /* ---- measurement helper: dependent-free DFMA stream, returns achieved fp64 FLOP/s (2 per DFMA).
  * bench.py uses it as the denominator "of self-measured DFMA peak" (MEASURED_PEAKS.json has no fp64
  * figure).  Synchronises. */

@@ -44,6 +44,14 @@ int bandpass_launch(int P, int C, int S, int A, const double* in, const double* 
 int dfma_peak(double* flops, double* mhz);
 int stats_launch(int T, long long M, const double* values, const double* refs, double* bias,
                  double* sd, double* rmse, double* nvalid, cudaStream_t st);
+int thin_mean_launch(int S, int N, int M, const double* h, const double* t, const double* p,
+                     const double* rh, const int* inds, const int* n_inds, const double* z_offset,
+                     double* zo, double* to, double* po, double* ro, cudaStream_t st);
+int assemble_launch(int S, int M, int K, int n_levels, double min_p, const double* zt, const double* tt,
+                    const double* pt, const double* rt, const int* n_inds, const double* cz_km,
+                    const double* cp, const double* ct, const double* cgkg, const double* crh,
+                    double* o_p, double* o_t, double* o_ppmv, double* o_h2o, double* o_z, double* o_rh,
+                    int* ok, cudaStream_t st);
 
 struct mwrt_builtin_model {
   const char* name;
@@ -580,6 +588,29 @@ int mwrt_stats_f64(int T, int64_t M, const double* values, const double* refs, d
   if (T <= 0 || M <= 0 || !values || !refs || !bias || !std || !rmse)
     return fail_arg(MWRT_E_ARG, "mwrt_stats_f64: bad argument");
   return stats_launch(T, M, values, refs, bias, std, rmse, n_valid, (cudaStream_t)stream);
+}
+
+int mwrt_thin_mean_f64(int S, int N, int M, const double* h, const double* t, const double* p,
+                       const double* rh, const int32_t* inds, const int32_t* n_inds,
+                       const double* z_offset, double* z_out, double* t_out, double* p_out,
+                       double* rh_out, void* stream) {
+  if (S <= 0 || N <= 0 || M <= 0 || !h || !t || !p || !rh || !inds || !n_inds || !z_out || !t_out ||
+      !p_out || !rh_out)
+    return fail_arg(MWRT_E_ARG, "mwrt_thin_mean_f64: bad argument");
+  return thin_mean_launch(S, N, M, h, t, p, rh, inds, n_inds, z_offset, z_out, t_out, p_out, rh_out,
+                          (cudaStream_t)stream);
+}
+
+int mwrt_assemble_levels_f64(int S, int M, int K, int n_levels, double min_p, const double* z,
+                             const double* t, const double* p, const double* rh, const int32_t* n_inds,
+                             const double* cz_km, const double* cp, const double* ct, const double* cgkg,
+                             const double* crh, double* o_p, double* o_t, double* o_ppmv, double* o_h2o,
+                             double* o_z, double* o_rh, int32_t* ok, void* stream) {
+  if (S <= 0 || M <= 0 || K <= 0 || n_levels < 180 || !z || !t || !p || !rh || !n_inds || !cz_km || !cp ||
+      !ct || !cgkg || !crh || !o_p || !o_t || !o_ppmv || !o_h2o || !o_z || !o_rh)
+    return fail_arg(MWRT_E_ARG, "mwrt_assemble_levels_f64: bad argument (n_levels >= 180 required)");
+  return assemble_launch(S, M, K, n_levels, min_p, z, t, p, rh, n_inds, cz_km, cp, ct, cgkg, crh, o_p,
+                         o_t, o_ppmv, o_h2o, o_z, o_rh, ok, (cudaStream_t)stream);
 }
 
 int mwrt_measure_dfma_peak(double* flops_per_s, double* sm_clock_mhz_est) {

@@ -160,3 +160,115 @@ def test_cloudy_wiring_from_level_liquid(built_lib):
     ref = ref.reshape(T, C, 14, 2).transpose(0, 2, 3, 1)
     assert (d["denliq"] > 0).any()
     assert np.max(np.abs(got - ref)) < 1e-3
+
+
+# ---- N1: profile pre-processing (thinning, running means, climatology top-up, lowest-180) ----------
+GOLD_PRE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "preproc_reference.npz")
+_LEVEL_KEYS = ("p", "t", "ppmv", "h2o_gkg", "z", "rh")
+
+
+def _pre_cases():
+    g = np.load(GOLD_PRE)
+    clim = {k: g["clim_" + k] for k in ("z_km", "p", "t", "gkg", "rh")}
+    return g, clim, list(zip(g["keys"], g["rejected"]))
+
+
+def test_preproc_oracle_equals_reference_output():
+    """oracle/preproc.py == the reference's own functions (outputs recorded by
+    tests/golden/make_preproc_golden.py from /root/reference's preprocessing4all.py): bit-exact."""
+    from oracle import preproc as op
+    g, clim, cases = _pre_cases()
+    seen_10hpa = False
+    for key, rej in cases:
+        h, t, p, rh = g[key.rstrip("v") + "_raw"]
+        inds = op.thinning_indices(h, p)
+        r = op.assemble_levels(h, t, p, rh, inds, clim, z_offset=20.0 if key.endswith("v") else 0.0)
+        assert r["ok"] == (not rej)
+        if rej:
+            assert all(np.isnan(r[k]).all() for k in _LEVEL_KEYS)
+            continue
+        zt, tt, pt, rt = g[key + "_thinned"]
+        assert np.array_equal(h[inds] - (20.0 if key.endswith("v") else 0.0), zt)
+        assert np.array_equal(op.running_mean_from_arrays(inds, t), tt, equal_nan=True)
+        got = np.stack([r[k] for k in _LEVEL_KEYS])
+        assert np.array_equal(got, g[key + "_levels"], equal_nan=True), key
+        # lowest2tenhPa fired if the 7 topmost kept levels are not a contiguous run of the column
+        seen_10hpa = seen_10hpa or got[0, 0] < 10.0
+    assert seen_10hpa
+
+
+def test_preproc_host_logic_matches_oracle():
+    from oracle import preproc as op
+    from mwr_fast_forward_operators_and_lbls_b200 import preproc as pp
+    g, clim, cases = _pre_cases()
+    for key, _ in cases:
+        h, t, p, rh = g[key.rstrip("v") + "_raw"]
+        assert op.detect_crop(h) == pp.detect_crop(h)
+        a, b = op.thinning_indices(h, p), pp.thinning_indices(h, p)
+        assert np.array_equal(a, b)
+    short = g["c0_raw"][:, :250]          # fewer than 300 usable samples -> rejected (:246)
+    assert pp.thinning_indices(short[0], short[2]) is None and op.thinning_indices(short[0], short[2]) is None
+    low = g["c0_raw"][:, :900]            # 10 km not reached (:251)
+    assert pp.thinning_indices(low[0], low[2]) is None
+    # the climatology the product ships is the one the goldens were generated with
+    c = pp.midlatitude_summer()
+    assert all(np.array_equal(c[k], clim[k]) for k in clim)
+
+
+@pytest.mark.gpu
+def test_preproc_gpu_vs_reference_output(built_lib):
+    """CUDA thinning/assembly vs the reference's recorded outputs and vs the oracle."""
+    from mwr_fast_forward_operators_and_lbls_b200 import preproc as pp
+    g, clim, cases = _pre_cases()
+    N = max(g[k + "_raw"].shape[1] for k, _ in cases if not k.endswith("v"))
+
+    def pad(a):
+        return np.concatenate([a, np.full(N - a.size, np.nan)])
+    raws = [g[k.rstrip("v") + "_raw"] for k, _ in cases]
+    H, T, P, R = (np.stack([pad(r[i]) for r in raws]) for i in range(4))
+    vital = np.array([k.endswith("v") for k, _ in cases])
+    out = pp.preprocess_sondes(H, T, P, R, vital=vital)
+    ok = out["ok"].cpu().numpy()
+    names = ("Level_Pressure", "Level_Temperature", "Level_ppmvs", "Level_H2O", "Level_z", "Level_RH")
+    for s, (key, rej) in enumerate(cases):
+        assert ok[s] == (0 if rej else 1)
+        got = np.stack([out[n][s].cpu().numpy() for n in names])
+        if rej:
+            assert np.isnan(got).all()
+            continue
+        ref = g[key + "_levels"]
+        assert np.array_equal(np.isnan(got), np.isnan(ref))
+        m = ~np.isnan(ref)
+        rel = np.abs(got[m] - ref[m]) / np.maximum(np.abs(ref[m]), 1e-300)
+        assert rel.max() < 1e-12, (key, rel.max())
+        n = int(out["thinned"]["n"][s])
+        th = np.stack([out["thinned"][k][s, :n].cpu().numpy() for k in ("z", "t", "p", "rh")])
+        rt = g[key + "_thinned"]
+        if np.all(th[3] <= 1.5):          # the reference returns RH already scaled to % (:299-300);
+            th[3] = th[3] * 100           # the device applies that scaling in the assembly kernel
+        assert np.array_equal(th[0], rt[0])
+        mm = ~np.isnan(rt)
+        assert np.array_equal(np.isnan(th), np.isnan(rt))
+        assert (np.abs(th[mm] - rt[mm]) <= 1e-13 * np.abs(rt[mm])).all()
+
+
+@pytest.mark.gpu
+def test_preproc_feeds_the_forward_model(built_lib):
+    """N1 -> hot path: Level_* from the device pre-processing go straight into the batched driver
+    (top-first, %, m) and give the TBs the oracle gets from the reference-recorded levels."""
+    from mwr_fast_forward_operators_and_lbls_b200 import preproc as pp, driver
+    import mwr_fast_forward_operators_and_lbls_b200 as pkg
+    from oracle import pyrtlib_vec as pv
+    g, clim, cases = _pre_cases()
+    h, t, p, rh = g["c0_raw"]
+    out = pp.preprocess_sondes(h[None], t[None], p[None], rh[None])
+
+    def lay(name):   # (1,180) top-first -> (180, time=1, Crop=1)
+        return out[name][0].cpu().numpy().reshape(180, 1, 1)
+    elev = np.array([90.0, 30.0, 4.2])
+    got = driver.derive_tbs_arrays(lay("Level_z"), lay("Level_Pressure"), lay("Level_Temperature"),
+                                   lay("Level_RH"), elevations=elev, models=("R24",))["R24"]
+    lv = g["c0_levels"]
+    ref = pv.simulate(lv[4][::-1][None] / 1000.0, lv[0][::-1][None], lv[1][::-1][None],
+                      lv[5][::-1][None] / 100.0, pkg.HATPRO_FRQ, elev, "R24")["tbtotal"]
+    assert np.max(np.abs(got[0, :, :, 0] - ref[0])) < 1e-3
