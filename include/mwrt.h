@@ -209,6 +209,16 @@ int mwrt_assemble_levels_f64(int S, int M, int K, int n_levels, double min_p, co
  * figure).  Synchronises. */
 int mwrt_measure_dfma_peak(double* flops_per_s, double* sm_clock_mhz_est);
 
+/* ---- test helper: the device math helpers the kernels are built from (branch-free exp/log with and
+ * without tables, MUFU+Newton reciprocal), evaluated elementwise so tests can check them against
+ * libm.  x, y: device, n doubles.  Domain as documented in csrc/mwrt_common.cuh. */
+#define MWRT_MATH_EXP_NB 0
+#define MWRT_MATH_EXP_TB 1
+#define MWRT_MATH_LOG_NB 2
+#define MWRT_MATH_LOG_TB 3
+#define MWRT_MATH_RCP 4
+int mwrt_math_selftest_f64(int op, int64_t n, const double* x, double* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

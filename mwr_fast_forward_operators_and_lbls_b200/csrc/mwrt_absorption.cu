@@ -23,6 +23,8 @@
 
 namespace mwrt {
 
+#define exp_tb_(x) exp_tb((x), etab)   // etab: the kernel's shared-memory exp table
+
 constexpr int kAbsThreads = 128;
 constexpr int kAllIn = 0, kAllOut = 1, kWing1Out = 2, kMixed = 3;
 
@@ -182,6 +184,10 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
   double* dminh = fsq + FB;               // nh: min_j |f_j - fl_i|
   double* dmino = dminh + nh;             // no: min_j |f_j - f_k|
   int* hcls = reinterpret_cast<int*>(dmino + no);   // nh: H2O line class w.r.t. the 750 GHz cutoff
+  __shared__ double etab[64];               // exp_tb / log_tb tables (mwrt_common.cuh)
+  __shared__ __align__(16) double ltab[128];
+  exp_tab_stage(etab);
+  log_tab_stage(ltab);
   const int f0 = blockIdx.y * FB;
   for (int i = threadIdx.x; i < m.n_table; i += blockDim.x) tab[i] = m.tables[i];
   if (threadIdx.x < FB) {
@@ -269,32 +275,32 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     const double pda = pp - pvap;
     const double den = m.h2o_den_const * rho;
     const double tic = div_fast(m.h2o_reftcon, t);
-    const double ticln = log_nb(tic);
+    const double ticln = log_tb(tic, ltab);
     const double conbase =
-        (m.h2o_cf * pda * exp_nb(m.h2o_xcf * ticln) + m.h2o_cs * pvap * exp_nb(m.h2o_xcs * ticln)) * pvap;
+        (m.h2o_cf * pda * exp_tb_(m.h2o_xcf * ticln) + m.h2o_cs * pvap * exp_tb_(m.h2o_xcs * ticln)) * pvap;
     const double ti = div_fast(m.h2o_reftline, t);
-    const double tiln = log_nb(ti);
+    const double tiln = log_tb(ti, ltab);
     const double omti = 1.0 - ti;
     const double* H = tab;
     const bool sd_on = m.h2o_sd != 0;
 
     auto hoist = [&](int i) {
       H2OLine h;
-      h.w = H[MWRT_H2O_W0 * nh + i] * pda * exp_nb(H[MWRT_H2O_X * nh + i] * tiln) +
-            H[MWRT_H2O_W0S * nh + i] * pvap * exp_nb(H[MWRT_H2O_XS * nh + i] * tiln);
+      h.w = H[MWRT_H2O_W0 * nh + i] * pda * exp_tb_(H[MWRT_H2O_X * nh + i] * tiln) +
+            H[MWRT_H2O_W0S * nh + i] * pvap * exp_tb_(H[MWRT_H2O_XS * nh + i] * tiln);
       // ti^0 = 1 exactly: most lines have no shift exponent, skip their exp (warp-uniform branch)
       double shf = H[MWRT_H2O_SH * nh + i] * pda * (1.0 - H[MWRT_H2O_AAIR * nh + i] * tiln);
       double shs = H[MWRT_H2O_SHS * nh + i] * pvap * (1.0 - H[MWRT_H2O_ASELF * nh + i] * tiln);
       const double xh = H[MWRT_H2O_XH * nh + i], xhs = H[MWRT_H2O_XHS * nh + i];
-      if (xh != 0.0) shf *= exp_nb(xh * tiln);
-      if (xhs != 0.0) shs *= exp_nb(xhs * tiln);
+      if (xh != 0.0) shf *= exp_tb_(xh * tiln);
+      if (xhs != 0.0) shs *= exp_tb_(xhs * tiln);
       h.shift = H[MWRT_H2O_SR * nh + i] * h.w + shf + shs;
       h.w2 = sd_on ? H[MWRT_H2O_W2 * nh + i] * pda + H[MWRT_H2O_W2S * nh + i] * pvap : 0.0;
       h.dl2 = sd_on ? H[MWRT_H2O_D2 * nh + i] * pda + H[MWRT_H2O_D2S * nh + i] * pvap : 0.0;
       h.wsq = h.w * h.w;
       h.base = h.w * rcp_fast(562500.0 + h.wsq);
       // strength with (1/fl)^2 folded in; the common f^2 is applied once at the end
-      h.sp = H[MWRT_H2O_S1 * nh + i] * exp_nb(fma(2.5, tiln, H[MWRT_H2O_B2 * nh + i] * omti)) * ifl2[i];
+      h.sp = H[MWRT_H2O_S1 * nh + i] * exp_tb_(fma(2.5, tiln, H[MWRT_H2O_B2 * nh + i] * omti)) * ifl2[i];
       // fast pair form: sp*w*(D0+D1)/(D0 D1) = (n1*vv + n0) / (vv^2 + c4)
       const double fc = H[MWRT_H2O_FL * nh + i] + h.shift;
       const double fc2 = fc * fc;
@@ -412,8 +418,8 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
   {
     const double th = div_fast(300.0, t);
     const double th1 = th - 1.0;
-    const double thln = log_nb(th);
-    const double b = exp_nb(m.o2_x * thln);
+    const double thln = log_tb(th, ltab);
+    const double b = exp_tb_(m.o2_x * thln);
     const double preswv = div_fast(rho * t, m.o2_pvap_div);
     const double presda = pp - preswv;
     const double den = 0.001 * (presda * b + m.o2_h2o_broad * preswv * th);
@@ -458,7 +464,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
       double ea[G], ev[G];
 #pragma unroll
       for (int g = 0; g < G; ++g) ea[g] = -O[MWRT_O2_BE * no + (k0 + g < no ? k0 + g : no - 1)] * th1;
-      exp_nb_vec<G>(ea, ev);
+      exp_tb_vec<G>(ea, ev, etab);
 #pragma unroll 1
       for (int gi = 0; gi < G; ++gi) {
       const int k = k0 + gi;
@@ -502,7 +508,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     }     // groups
     const double scale = m.o2_abs_const * presda * (th * th * th);
     const double pdry_mb = pdrykpa * 10.0;
-    const double n2base = m.n2_n * (m.n2_l * pdry_mb * pdry_mb * exp_nb(m.n2_m * thln));
+    const double n2base = m.n2_n * (m.n2_l * pdry_mb * pdry_mb * exp_tb_(m.n2_m * thln));
 #pragma unroll
     for (int j = 0; j < FB; ++j) {
       const double f = fblk[j];

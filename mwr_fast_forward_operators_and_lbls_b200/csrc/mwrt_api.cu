@@ -53,6 +53,8 @@ int assemble_launch(int S, int M, int K, int n_levels, double min_p, const doubl
                     double* o_p, double* o_t, double* o_ppmv, double* o_h2o, double* o_z, double* o_rh,
                     int* ok, cudaStream_t st);
 
+int math_selftest_launch(int op, long long n, const double* x, double* y, cudaStream_t st);
+
 struct mwrt_builtin_model {
   const char* name;
   mwrt_model_desc desc;
@@ -611,6 +613,12 @@ int mwrt_assemble_levels_f64(int S, int M, int K, int n_levels, double min_p, co
     return fail_arg(MWRT_E_ARG, "mwrt_assemble_levels_f64: bad argument (n_levels >= 180 required)");
   return assemble_launch(S, M, K, n_levels, min_p, z, t, p, rh, n_inds, cz_km, cp, ct, cgkg, crh, o_p,
                          o_t, o_ppmv, o_h2o, o_z, o_rh, ok, (cudaStream_t)stream);
+}
+
+int mwrt_math_selftest_f64(int op, int64_t n, const double* x, double* y, void* stream) {
+  if (n <= 0 || !x || !y || op < 0 || op > MWRT_MATH_RCP)
+    return fail_arg(MWRT_E_ARG, "mwrt_math_selftest_f64: bad argument");
+  return math_selftest_launch(op, n, x, y, (cudaStream_t)stream);
 }
 
 int mwrt_measure_dfma_peak(double* flops_per_s, double* sm_clock_mhz_est) {

@@ -174,6 +174,160 @@ __device__ __forceinline__ void rcp_fast_vec(const double (&x)[N], double (&y)[N
   for (int a = 0; a < N; ++a) MWRT_FMA(y[a], r[a], e[a], r[a]);
 }
 
+// ---- table-driven exp: 10 FP64-pipe instructions -----------------------------------------------
+// exp(x) = 2^k * T[j] * exp(r),  n = round(x*64/ln2) = 64 k + j,  r = x - n*ln2/64, |r| <= ln2/128:
+// exp(r)-1 needs only degree 5 (r^6/720 < 3.5e-17), T[j] = 2^(j/64) correctly rounded, read from a
+// 64-entry shared-memory table (one LDS.64; the LSU pipe is idle in both hot kernels).  Same domain as
+// exp_nb (|x| < 700, no NaN/inf/denormal handling); result within ~1 ulp.
+static __device__ const double kExpTab64[64] = {
+    0x1.0000000000000p+0, 0x1.02c9a3e778061p+0, 0x1.059b0d3158574p+0, 0x1.0874518759bc8p+0,
+    0x1.0b5586cf9890fp+0, 0x1.0e3ec32d3d1a2p+0, 0x1.11301d0125b51p+0, 0x1.1429aaea92de0p+0,
+    0x1.172b83c7d517bp+0, 0x1.1a35beb6fcb75p+0, 0x1.1d4873168b9aap+0, 0x1.2063b88628cd6p+0,
+    0x1.2387a6e756238p+0, 0x1.26b4565e27cddp+0, 0x1.29e9df51fdee1p+0, 0x1.2d285a6e4030bp+0,
+    0x1.306fe0a31b715p+0, 0x1.33c08b26416ffp+0, 0x1.371a7373aa9cbp+0, 0x1.3a7db34e59ff7p+0,
+    0x1.3dea64c123422p+0, 0x1.4160a21f72e2ap+0, 0x1.44e086061892dp+0, 0x1.486a2b5c13cd0p+0,
+    0x1.4bfdad5362a27p+0, 0x1.4f9b2769d2ca7p+0, 0x1.5342b569d4f82p+0, 0x1.56f4736b527dap+0,
+    0x1.5ab07dd485429p+0, 0x1.5e76f15ad2148p+0, 0x1.6247eb03a5585p+0, 0x1.6623882552225p+0,
+    0x1.6a09e667f3bcdp+0, 0x1.6dfb23c651a2fp+0, 0x1.71f75e8ec5f74p+0, 0x1.75feb564267c9p+0,
+    0x1.7a11473eb0187p+0, 0x1.7e2f336cf4e62p+0, 0x1.82589994cce13p+0, 0x1.868d99b4492edp+0,
+    0x1.8ace5422aa0dbp+0, 0x1.8f1ae99157736p+0, 0x1.93737b0cdc5e5p+0, 0x1.97d829fde4e50p+0,
+    0x1.9c49182a3f090p+0, 0x1.a0c667b5de565p+0, 0x1.a5503b23e255dp+0, 0x1.a9e6b5579fdbfp+0,
+    0x1.ae89f995ad3adp+0, 0x1.b33a2b84f15fbp+0, 0x1.b7f76f2fb5e47p+0, 0x1.bcc1e904bc1d2p+0,
+    0x1.c199bdd85529cp+0, 0x1.c67f12e57d14bp+0, 0x1.cb720dcef9069p+0, 0x1.d072d4a07897cp+0,
+    0x1.d5818dcfba487p+0, 0x1.da9e603db3285p+0, 0x1.dfc97337b9b5fp+0, 0x1.e502ee78b3ff6p+0,
+    0x1.ea4afa2a490dap+0, 0x1.efa1bee615a27p+0, 0x1.f50765b6e4540p+0, 0x1.fa7c1819e90d8p+0};
+constexpr double kExp64InvLn2 = 0x1.71547652b82fep+6;   // 64/ln2
+constexpr double kExpLn2o64Hi = 0x1.62e42fe000000p-7;   // ln2/64, 28 significant bits: n*hi is exact
+constexpr double kExpLn2o64Lo = 0x1.f473de6af278fp-36;
+
+// every thread of the CTA calls this once, before a __syncthreads(), to stage the table
+__device__ __forceinline__ void exp_tab_stage(double* tab) {
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) tab[i] = kExpTab64[i];
+}
+
+__device__ __forceinline__ double exp_tb(double x, const double* __restrict__ tab) {
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
+  double t = fma(x, kExp64InvLn2, kMagic);
+  const int n = __double2loint(t);
+  t -= kMagic;
+  double r = fma(-t, kExpLn2o64Hi, x);
+  r = fma(-t, kExpLn2o64Lo, r);
+  const double T = tab[n & 63];
+  double p = fma(r, 8.333333333333333e-03, 4.1666666666666664e-02);
+  p = fma(p, r, 1.6666666666666666e-01);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(T, p * r, T);
+  return __hiloint2double(__double2hiint(p) + ((n >> 6) << 20), __double2loint(p));
+}
+
+// N independent arguments, stage by stage (see exp_nb_vec)
+template <int N>
+__device__ __forceinline__ void exp_tb_vec(const double (&x)[N], double (&y)[N],
+                                           const double* __restrict__ tab) {
+  const double kMagic = 6755399441055744.0;
+  double t[N], r[N], p[N], T[N];
+  int n[N];
+#pragma unroll
+  for (int a = 0; a < N; ++a) MWRT_FMA(t[a], x[a], kExp64InvLn2, kMagic);
+#pragma unroll
+  for (int a = 0; a < N; ++a) {
+    n[a] = __double2loint(t[a]);
+    T[a] = tab[n[a] & 63];
+    MWRT_ADD(t[a], t[a], -kMagic);
+  }
+#pragma unroll
+  for (int a = 0; a < N; ++a) MWRT_FMA(r[a], t[a], -kExpLn2o64Hi, x[a]);
+#pragma unroll
+  for (int a = 0; a < N; ++a) MWRT_FMA(r[a], t[a], -kExpLn2o64Lo, r[a]);
+#pragma unroll
+  for (int a = 0; a < N; ++a) MWRT_FMA(p[a], r[a], 8.333333333333333e-03, 4.1666666666666664e-02);
+#pragma unroll
+  for (int a = 0; a < N; ++a) MWRT_FMA(p[a], p[a], r[a], 1.6666666666666666e-01);
+#pragma unroll
+  for (int a = 0; a < N; ++a) MWRT_FMA(p[a], p[a], r[a], 0.5);
+#pragma unroll
+  for (int a = 0; a < N; ++a) MWRT_FMA(p[a], p[a], r[a], 1.0);
+#pragma unroll
+  for (int a = 0; a < N; ++a) MWRT_MUL(p[a], p[a], r[a]);
+#pragma unroll
+  for (int a = 0; a < N; ++a) MWRT_FMA(p[a], T[a], p[a], T[a]);
+#pragma unroll
+  for (int a = 0; a < N; ++a)
+    y[a] = __hiloint2double(__double2hiint(p[a]) + ((n[a] >> 6) << 20), __double2loint(p[a]));
+}
+
+// ---- table-driven natural log: 14 FP64-pipe instructions ----------------------------------------
+// x = 2^e m, m in [1,2); i = top 6 mantissa bits.  Intervals i >= 27 (m >= 1.42) are taken as m/2 with
+// e+1, so the argument of the table step lies in [0.71, 1.42) and log x never cancels against e ln2.
+// Table (c_i, -log c_i): c_i ~ 1/m_centre to 12 bits, so r = fma(m, c_i, -1) is exact-rounded and
+// |r| <= 1/128; the two intervals touching 1 use c = 1 (r = m - 1 exactly, table term 0), so the
+// result keeps full RELATIVE accuracy as x -> 1.  log1p(r) to degree 9 (|r| <= 1/64: r^9/10 < 6e-18).
+// Domain: normal positive x (callers substitute a stand-in and select afterwards, like log_nb).
+static __device__ const double kLogTab64[128] = {
+    0x1.0000000000000p+0, 0x0.0p+0, 0x1.f440000000000p-1, 0x1.7c61b1cf5dee0p-6,
+    0x1.ecc0000000000p-1, 0x1.39f07ba0ebd62p-5, 0x1.e580000000000p-1, 0x1.b35dd9b58baadp-5,
+    0x1.de60000000000p-1, 0x1.163d6ef957a03p-4, 0x1.d780000000000p-1, 0x1.518874226130ap-4,
+    0x1.d0c0000000000p-1, 0x1.8c985e9b9ec84p-4, 0x1.ca40000000000p-1, 0x1.c6494a2e418a6p-4,
+    0x1.c400000000000p-1, 0x1.fe89139dbd566p-4, 0x1.bde0000000000p-1, 0x1.1b35ae3b81dbfp-3,
+    0x1.b7e0000000000p-1, 0x1.36f4c27577593p-3, 0x1.b200000000000p-1, 0x1.527e5e4a1b58dp-3,
+    0x1.ac60000000000p-1, 0x1.6d35fee52b83bp-3, 0x1.a6e0000000000p-1, 0x1.87ad07c493478p-3,
+    0x1.a160000000000p-1, 0x1.a27cc30640ecbp-3, 0x1.9c20000000000p-1, 0x1.bc69684aee63ep-3,
+    0x1.9700000000000p-1, 0x1.d60a17f903515p-3, 0x1.9200000000000p-1, 0x1.ef5ade4dcffe6p-3,
+    0x1.8d40000000000p-1, 0x1.03d95a1d67686p-2, 0x1.8860000000000p-1, 0x1.107e404ab0f81p-2,
+    0x1.83c0000000000p-1, 0x1.1ca28c64bae54p-2, 0x1.7f40000000000p-1, 0x1.2896a13e086a4p-2,
+    0x1.7ae0000000000p-1, 0x1.34585a594b8adp-2, 0x1.7680000000000p-1, 0x1.403d086cea79cp-2,
+    0x1.7240000000000p-1, 0x1.4becf95d97913p-2, 0x1.6e20000000000p-1, 0x1.5765f1749da6bp-2,
+    0x1.6a20000000000p-1, 0x1.62a5afc06121fp-2, 0x1.6620000000000p+0, -0x1.57c2f53b05209p-2,
+    0x1.6240000000000p+0, -0x1.4c9f09e152c3cp-2, 0x1.5e80000000000p+0, -0x1.41b941cce0beep-2,
+    0x1.5ac0000000000p+0, -0x1.36b5776bc1117p-2, 0x1.5720000000000p+0, -0x1.2bf287cc41362p-2,
+    0x1.53a0000000000p+0, -0x1.2172d5c2abbbbp-2, 0x1.5020000000000p+0, -0x1.16d74c2e8ac66p-2,
+    0x1.4ca0000000000p+0, -0x1.0c1f55d88a8a1p-2, 0x1.4960000000000p+0, -0x1.021164a9290ddp-2,
+    0x1.4600000000000p+0, -0x1.ef0adcbdc5936p-3, 0x1.42e0000000000p+0, -0x1.db50da24bd322p-3,
+    0x1.3fc0000000000p+0, -0x1.c765b9e4d68d6p-3, 0x1.3ca0000000000p+0, -0x1.b34885022e81ep-3,
+    0x1.39a0000000000p+0, -0x1.9fc93e5409c31p-3, 0x1.36a0000000000p+0, -0x1.8c19fe2982058p-3,
+    0x1.33a0000000000p+0, -0x1.7839d62023552p-3, 0x1.30e0000000000p+0, -0x1.65d5e99cc3c47p-3,
+    0x1.2e00000000000p+0, -0x1.526e5e3a1b438p-3, 0x1.2b40000000000p+0, -0x1.3fb25a59528cbp-3,
+    0x1.2880000000000p+0, -0x1.2cca0f5f5f251p-3, 0x1.25e0000000000p+0, -0x1.1a93b7d42f611p-3,
+    0x1.2340000000000p+0, -0x1.08338affa282ap-3, 0x1.20c0000000000p+0, -0x1.ed1794e83780cp-4,
+    0x1.1e20000000000p+0, -0x1.c7af7a8472d76p-4, 0x1.1bc0000000000p+0, -0x1.a58b60c2b2324p-4,
+    0x1.1940000000000p+0, -0x1.814be23f8c036p-4, 0x1.16e0000000000p+0, -0x1.5e8fa4d8591c7p-4,
+    0x1.1480000000000p+0, -0x1.3b87598b1b6eep-4, 0x1.1240000000000p+0, -0x1.1a0fba1bf8a52p-4,
+    0x1.0fe0000000000p+0, -0x1.ecdf0f87b6168p-5, 0x1.0dc0000000000p+0, -0x1.ac97221711f8dp-5,
+    0x1.0b80000000000p+0, -0x1.67f94f094bd98p-5, 0x1.0960000000000p+0, -0x1.26a32a86d2f72p-5,
+    0x1.0740000000000p+0, -0x1.c98d18d00c814p-6, 0x1.0520000000000p+0, -0x1.44c28d451662cp-6,
+    0x1.0300000000000p+0, -0x1.7dc475f810a77p-7, 0x1.0000000000000p+0, 0x0.0p+0};
+
+__device__ __forceinline__ void log_tab_stage(double* tab) {
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) tab[i] = kLogTab64[i];
+}
+
+__device__ __forceinline__ double log_tb(double x, const double* __restrict__ tab) {
+  int hi = __double2hiint(x);
+  const int lo = __double2loint(x);
+  int e = (hi >> 20) - 1023;
+  const int i = (hi >> 14) & 63;
+  const bool big = i >= 27;
+  hi = (hi & 0x000fffff) | (big ? 0x3fe00000 : 0x3ff00000);   // m or m/2
+  e = big ? e + 1 : e;
+  const double m = __hiloint2double(hi, lo);
+  const double2 cl = *reinterpret_cast<const double2*>(tab + 2 * i);
+  const double r = fma(m, cl.x, -1.0);
+  const double r2 = r * r;
+  double q = 1.0 / 9.0;
+  q = fma(q, r, -1.0 / 8.0);
+  q = fma(q, r, 1.0 / 7.0);
+  q = fma(q, r, -1.0 / 6.0);
+  q = fma(q, r, 1.0 / 5.0);
+  q = fma(q, r, -1.0 / 4.0);
+  q = fma(q, r, 1.0 / 3.0);
+  q = fma(q, r, -0.5);
+  const double ed = (double)e;
+  const double tail = fma(r2, q, ed * 1.90821492927058770002e-10);
+  const double head = fma(ed, 6.93147180369123816490e-01, cl.y);
+  return head + (r + tail);
+}
+
 // ---- minimal complex arithmetic (speed-dependent line shape, liquid permittivity) -----------
 struct cplx {
   double re, im;

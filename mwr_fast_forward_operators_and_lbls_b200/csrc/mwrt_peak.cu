@@ -73,4 +73,34 @@ int dfma_peak(double* flops, double* mhz) {
   return 0;
 }
 
+
+// Elementwise evaluation of the device math helpers, for the unit tests (tests/test_gpu_parity.py).
+__global__ void k_math_selftest(const int op, const long long n, const double* __restrict__ x,
+                                double* __restrict__ y) {
+  __shared__ double etab[64];
+  __shared__ double ltab[2 * 64];
+  exp_tab_stage(etab);
+  log_tab_stage(ltab);
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = x[i];
+  double r;
+  switch (op) {
+    case MWRT_MATH_EXP_NB: r = exp_nb(v); break;
+    case MWRT_MATH_EXP_TB: r = exp_tb(v, etab); break;
+    case MWRT_MATH_LOG_NB: r = log_nb(v); break;
+    case MWRT_MATH_LOG_TB: r = log_tb(v, ltab); break;
+    case MWRT_MATH_RCP: r = rcp_fast(v); break;
+    default: r = nan("");
+  }
+  y[i] = r;
+}
+
+int math_selftest_launch(int op, long long n, const double* x, double* y, cudaStream_t st) {
+  k_math_selftest<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, n, x, y);
+  MWRT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace mwrt

@@ -21,13 +21,15 @@ constexpr int kRteThreads = 128;
 // x1 = upper level.  Branch-free (selects) so the caller's layer loop stays one basic block:
 //   negative input -> NaN and `neg` (PyRTlib raises ValueError; the profile gets MWRT_ST_NEG_ABS)
 //   |x1-x0| < 1e-9 -> x1;  a zero endpoint -> mean (zeroflg) or 0;  else (x1-x0)/log(x1/x0).
-__device__ __forceinline__ double layer_mean(double x0, double x1, bool zeroflg, bool& neg) {
+__device__ __forceinline__ double layer_mean(double x0, double x1, bool zeroflg, bool& neg,
+                                             const double* __restrict__ ltab) {
   const bool negv = (x0 < 0.0) || (x1 < 0.0);
   const bool close = fabs(x1 - x0) < 1e-09;
   const bool zero = (x0 == 0.0) || (x1 == 0.0);
   const bool use_log = !(negv || close || zero) && (x0 > 0.0) && (x1 > 0.0);  // false for NaN too
   const double a = use_log ? x1 : 2.0, bq = use_log ? x0 : 1.0;              // keeps log_nb's domain
-  const double lm = div_fast(x1 - x0, log_nb(div_fast(a, bq)));
+  // reciprocal-multiply (<= 1.5 ulp each) instead of corrected divisions: 4 FP64 instructions fewer
+  const double lm = (x1 - x0) * rcp_fast(log_tb(a * rcp_fast(bq), ltab));
   double r = zero ? (zeroflg ? (x1 + x0) * 0.5 : 0.0) : lm;
   r = close ? x1 : r;
   r = (negv || !(use_log || close || zero)) ? nan("") : r;
@@ -37,19 +39,19 @@ __device__ __forceinline__ double layer_mean(double x0, double x1, bool zeroflg,
 
 // modified Planck function 1/(exp(hvk/T) - 1); hvk/T is O(1e-2) for microwave frequencies.
 // T is a physical temperature here (kernel 1 flags anything outside 50..1000 K), hvk/T < 700.
-__device__ __forceinline__ double planck_mod(double hvk, double t) {
-  const double x = div_fast(hvk, t);
-  return rcp_fast(exp_nb(fmax(fmin(x, 700.0), -700.0)) - 1.0);
+__device__ __forceinline__ double planck_mod(double hvk, double t, const double* __restrict__ etab) {
+  const double x = hvk * rcp_fast(t);
+  return rcp_fast(exp_tb(fmax(fmin(x, 700.0), -700.0), etab) - 1.0);
 }
 __device__ __forceinline__ double bright(double hvk, double b) {
   if (b > 0.0 || isnan(b)) return hvk / log(1.0 + 1.0 / b);
   return 0.0;
 }
 // bright() without library calls or branches: b <= 0 -> 0, NaN -> NaN, else hvk / log(1 + 1/b)
-__device__ __forceinline__ double bright_nb(double hvk, double b) {
+__device__ __forceinline__ double bright_nb(double hvk, double b, const double* __restrict__ ltab) {
   const bool pos = b > 0.0;
   const double x = 1.0 + rcp_fast(pos ? b : 1.0);
-  const double t = hvk * rcp_fast(log_nb(x));
+  const double t = hvk * rcp_fast(log_tb(x, ltab));
   return pos ? t : (isnan(b) ? b : 0.0);
 }
 
@@ -71,6 +73,11 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
       double* __restrict__ tmr, double* __restrict__ tauwet, double* __restrict__ taudry,
       double* __restrict__ tauliq, double* __restrict__ tauice, double* __restrict__ tau_layer,
       const int tl_angle, int* __restrict__ status) {
+  __shared__ double etab[64];        // exp_tb / log_tb tables (mwrt_common.cuh)
+  __shared__ __align__(16) double ltab[128];
+  exp_tab_stage(etab);
+  log_tab_stage(ltab);
+  __syncthreads();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)P * F) return;
   const long long p = idx / F;
@@ -94,6 +101,21 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
   }
 #pragma unroll
   for (int a = 0; a < NS; ++a) { sw[a] = 0.0; sd[a] = 0.0; sl[a] = 0.0; si[a] = 0.0; tauprof[a] = 0.0; }
+
+  // PLANE: one clamp per layer on the zenith optical depth instead of one per angle.  exp_tb needs
+  // tau < 700; capping the zenith value at 700/max(amass) changes exp(-tau) only where it is < 1e-21
+  // relative to the terms it is added to.
+  double tcap = 700.0;
+  if (PLANE) {
+    double amax = 1.0;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) amax = fmax(amax, fabs(amass[a]));
+    tcap = 700.0 / amax;
+  }
+  double tl_amass = 0.0;   // PLANE: air mass of the angle whose per-layer optical depths are wanted
+#pragma unroll
+  for (int a = 0; a < NA; ++a)
+    if (a0 + a == tl_angle) tl_amass = amass[a];
 
   bool neg = false, anynan = false;
   const bool want_tl = (tau_layer != nullptr) && (tl_angle >= a0) && (tl_angle < a0 + NA);
@@ -123,17 +145,17 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     const Lvl& lo = from_sat ? fr : nr;
     const Lvl& up = from_sat ? nr : fr;
     Lay y;
-    y.xw = layer_mean(lo.w, up.w, true, ng);
-    y.xd = layer_mean(lo.d, up.d, true, ng);
+    y.xw = layer_mean(lo.w, up.w, true, ng, ltab);
+    y.xd = layer_mean(lo.d, up.d, true, ng, ltab);
     y.xtot = y.xw + y.xd;
     y.xl = 0.0;
     y.xi = 0.0;
     if (CLOUDY) {
-      y.xl = layer_mean(lo.l, up.l, false, ng);
-      y.xi = layer_mean(lo.i, up.i, false, ng);
+      y.xl = layer_mean(lo.l, up.l, false, ng, ltab);
+      y.xi = layer_mean(lo.i, up.i, false, ng, ltab);
       y.xtot = y.xtot + y.xi + y.xl;
     }
-    y.bfar = planck_mod(hvk, fr.t);
+    y.bfar = planck_mod(hvk, fr.t, etab);
     y.dz = up.z - lo.z;
     nn = nn || isnan(y.xtot) || isnan(fr.t) || isnan(y.dz);
     return y;
@@ -141,7 +163,7 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
 
   Lvl lvA = load(lev0);
   anynan = isnan(lvA.t);
-  double bnear = planck_mod(hvk, lvA.t);
+  double bnear = planck_mod(hvk, lvA.t, etab);
   Lvl lvB = load(lev0 + dir);
   Lay cur = prep(lvA, lvB, neg, anynan);
   lvA = lvB;
@@ -169,23 +191,29 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     }
     // per-angle work, written stage by stage over the NA angles (see exp_nb_vec)
     double tau[NA], ntau[NA], ex[NA], den[NA], rden[NA];
+    if (PLANE) {
+      const double t0 = xtot * dz;                 // zenith optical depth of the layer
+      const double t0n = -fmin(t0, tcap);          // NaN is caught by `anynan`
 #pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      double dsa;
-      if (PLANE) {
-        dsa = dz * amass[a];
-      } else {
-        dsa = (a0 + a < A) ? dsp[(long long)a * L + j] : 0.0;
+      for (int a = 0; a < NA; ++a) {
+        ntau[a] = t0n * amass[a];
+        tau[a] = 0.0;
+      }
+      if (want_tl) tau_layer[row + j] = t0 * tl_amass;
+    } else {
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        const double dsa = (a0 + a < A) ? dsp[(long long)a * L + j] : 0.0;
         sw[a] = fma(xw, dsa, sw[a]);
         sd[a] = fma(xd, dsa, sd[a]);
         if (CLOUDY) { sl[a] = fma(xl, dsa, sl[a]); si[a] = fma(xi, dsa, si[a]); }
+        tau[a] = xtot * dsa;
+        tauprof[a] += tau[a];
       }
-      tau[a] = xtot * dsa;
-      if (!PLANE) tauprof[a] += tau[a];
-    }
 #pragma unroll
-    for (int a = 0; a < NA; ++a) ntau[a] = fmax(-tau[a], -700.0);
-    exp_nb_vec<NA>(ntau, ex);
+      for (int a = 0; a < NA; ++a) ntau[a] = fmax(-tau[a], -700.0);
+    }
+    exp_tb_vec<NA>(ntau, ex, etab);
 #pragma unroll
     for (int a = 0; a < NA; ++a) den[a] = 1.0 + ex[a];
     rcp_fast_vec<NA>(den, rden);
@@ -195,7 +223,7 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
       batm[a] = fma(boftlay * trans[a], 1.0 - ex[a], batm[a]);
       trans[a] *= ex[a];
     }
-    if (want_tl) {
+    if (want_tl && !PLANE) {
       double tl = 0.0;
 #pragma unroll
       for (int a = 0; a < NA; ++a)
@@ -210,7 +238,7 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
   const bool bad = neg || anynan || flagged;
   if (status && neg) atomicOr(&status[p], MWRT_ST_NEG_ABS);
   if (status && anynan && !neg && !flagged && jf == 0 && a0 == 0) atomicOr(&status[p], MWRT_ST_NAN_INPUT);
-  const double bbg = from_sat ? emis * planck_mod(hvk, tkp[0]) : planck_mod(hvk, kTCosmic);
+  const double bbg = from_sat ? emis * planck_mod(hvk, tkp[0], etab) : planck_mod(hvk, kTCosmic, etab);
   const long long obase = idx * (long long)A + a0;
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
@@ -220,11 +248,11 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     // branch-free exp/log/reciprocal helpers: NA angles x 3 outputs would otherwise inline ~6000
     // instructions of library slow paths here
     const bool thin = tp < kExpMax;
-    const double et = exp_nb(fmax(-tp, -700.0));
+    const double et = exp_tb(fmax(-tp, -700.0), etab);
     const double boftotl = thin ? fma(bbg, et, batm[a]) : batm[a];
     const double boftmr = thin ? batm[a] * rcp_fast(1.0 - et) : batm[a];
-    const double o_tot = bright_nb(hvk, boftotl), o_atm0 = bright_nb(hvk, batm[a]);
-    const double o_mr0 = bright_nb(hvk, boftmr);
+    const double o_tot = bright_nb(hvk, boftotl, ltab), o_atm0 = bright_nb(hvk, batm[a], ltab);
+    const double o_mr0 = bright_nb(hvk, boftmr, ltab);
     double o_tot_ = o_tot, o_atm = o_atm0, o_mr = o_mr0;
     double o_w = PLANE ? sw[0] * amass[a] : sw[a], o_d = PLANE ? sd[0] * amass[a] : sd[a];
     double o_l = PLANE ? sl[0] * amass[a] : sl[a], o_i = PLANE ? si[0] * amass[a] : si[a];

@@ -292,3 +292,18 @@ def measure_dfma_peak():
     fl, mhz = C.c_double(), C.c_double()
     _lib.check(lib.mwrt_measure_dfma_peak(C.byref(fl), C.byref(mhz)), "measure_dfma_peak")
     return fl.value, mhz.value
+
+
+MATH_OPS = {"exp_nb": 0, "exp_tb": 1, "log_nb": 2, "log_tb": 3, "rcp": 4}
+
+
+def math_selftest(op, x):
+    """Evaluate one of the device math helpers (csrc/mwrt_common.cuh) elementwise -- test hook."""
+    _need_cuda()
+    lib = _lib.load()
+    xd = _dev64(x).contiguous()
+    y = torch.empty_like(xd)
+    _lib.check(lib.mwrt_math_selftest_f64(MATH_OPS[op], xd.numel(), _ptr(xd), _ptr(y), _stream()),
+               "math_selftest")
+    torch.cuda.current_stream().synchronize()
+    return y

@@ -345,3 +345,30 @@ def test_dense_spectrum_and_icon_shapes(pkg, ora):
 def test_dfma_peak_is_plausible(pkg):
     fl, mhz = pkg.measure_dfma_peak()
     assert 5e12 < fl < 6e13, fl      # B200 nominal 37.2 TFLOP/s fp64
+
+
+def test_device_math_helpers(pkg):
+    """The branch-free exp/log/reciprocal the kernels are built from, against libm, in ulps."""
+    from mwr_fast_forward_operators_and_lbls_b200.forward import math_selftest
+    rng = np.random.default_rng(11)
+
+    def ulps(got, ref):
+        return np.max(np.abs(got - ref) / np.spacing(np.abs(ref)))
+    x = np.concatenate([rng.uniform(-700, 700, 200000), rng.uniform(-1, 1, 200000),
+                        rng.uniform(-1e-3, 1e-3, 50000), [0.0, -0.0, 699.9, -699.9],
+                        (np.arange(-130, 131) * np.log(2) / 64)])
+    for op in ("exp_nb", "exp_tb"):
+        got = math_selftest(op, x).cpu().numpy()
+        assert ulps(got, np.exp(x)) <= 2.0, op
+    x = np.concatenate([np.exp(rng.uniform(-600, 600, 200000)), rng.uniform(0.5, 2.0, 200000),
+                        1.0 + rng.uniform(-1e-6, 1e-6, 50000), 1.0 + rng.uniform(-0.02, 0.02, 50000),
+                        [1.0, 2.0, 0.5, 1.0 + 27 / 64, np.nextafter(1.0 + 27 / 64, 0), np.nextafter(1.0, 0),
+                         np.nextafter(1.0, 2), np.nextafter(2.0, 0), 1e-300, 1e300]])
+    for op in ("log_nb", "log_tb"):
+        got = math_selftest(op, x).cpu().numpy()
+        ref = np.log(x)
+        nz = ref != 0.0
+        assert (got[~nz] == 0.0).all(), op
+        assert ulps(got[nz], ref[nz]) <= 2.5, op
+    x = np.concatenate([np.exp(rng.uniform(-300, 300, 200000)), -np.exp(rng.uniform(-300, 300, 1000))])
+    assert ulps(math_selftest("rcp", x).cpu().numpy(), 1.0 / x) <= 1.5
