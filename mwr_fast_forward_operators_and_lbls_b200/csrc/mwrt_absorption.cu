@@ -137,31 +137,40 @@ __device__ __noinline__ double liq_abs_unit(int liq_model, double f, double tk) 
 // Fast pair form used by both species.  With u = f^2, fc = line centre, w = half width:
 //   D1 D2 = ((f-fc)^2 + w^2)((f+fc)^2 + w^2) = (u - fc^2 + w^2)^2 + 4 fc^2 w^2 = vv^2 + c4,  vv = u - c3
 //   D1 + D2 = 2 (vv + 2 fc^2),   d1 D2 - d2 D1 = 2 fc (vv - 2 w^2)
-// so a line's two wings cost per frequency: 1 DADD (vv), 1 DFMA (D), 1 DFMA (numerator = n1*vv + n0),
-// one reciprocal (MUFU.RCP64H + 3 DFMA) and 1 DFMA to accumulate: 7 FP64-pipe instructions.
+// so a line's two wings are ONE fraction (n1*vv + n0)/(vv^2 + c4) per frequency, and two LINES a, b
+// share one reciprocal:  na/Da + nb/Db = (na Db + nb Da)/(Da Db):
+//   2 DADD (vv) + 2 DFMA (D) + 2 DFMA (n) + DMUL (Da Db) + DMUL, DFMA (numerator) + reciprocal
+//   (MUFU.RCP64H + 3 DFMA) + DFMA (accumulate) = 13 FP64-pipe instructions and 1 MUFU per
+//   (line pair, frequency), i.e. 6.5 per line instead of 7, with half the MUFU and f^2 loads.
 // Rounding: the only cancellation is in vv (relative error ~ eps*f/(2*max(|f-fc|, w))); lines that are
-// both narrower than 1e-3*fc and closer than 1e-3*fc to a frequency of the block take the exact
-// per-wing form in the rare-path loop instead.
+// both narrower than 1e-3*fc and closer than 1e-3*fc to a frequency of the block get the exact
+// per-wing form as a correction in the slow-path loop.
 struct H2OLine {
   double w, wsq, base, shift, sp, w2, dl2, c3, c4, n1, n0;
 };
 struct O2Line {
   double fcen, df, df2, sp, y, gfac, c3, c4, n1, n0;
 };
-// what the hot loops keep live per line (two copies: current + prefetched next); everything else is
-// recomputed in the rare path so that 14 running sums + two of these fit in 128 registers
-struct H2OHot {
-  double c3, c4, n1, n0, b2, w, shift, w2;
+struct PairHot {   // what the pair loop keeps live: 8 doubles
+  double c3a, c4a, n1a, n0a, c3b, c4b, n1b, n0b;
 };
-struct O2Hot {
-  double c3, c4, n1, n0, df, fcen;
-};
+
+// shared-memory line tables are LINE-major (one row per line, read with LDS.128 at immediate
+// offsets): the model's columns, then 1/f_line^2, padded to an even stride
+constexpr int kHS = MWRT_H2O_NCOL + 2;   // 20
+constexpr int kOS = MWRT_O2_NCOL + 2;    // 12
+constexpr int kH_IFL2 = MWRT_H2O_NCOL, kO_IFK2 = MWRT_O2_NCOL;
+static_assert(kHS % 2 == 0 && kOS % 2 == 0, "row strides must keep 16-byte alignment");
+constexpr int kSlowNone = 0, kSlowCorr = 1, kSlowExact = 2;
+
+__host__ __device__ inline int abs_smem_doubles(int nh, int no, int FB) {
+  const int nop = (no + 1) & ~1;
+  // hrow, orow, fblk, fsq, dfm, dfp, dminh, dmino, then ints: hcls[nh], hord[nh], cnt[2]
+  return nh * kHS + nop * kOS + 2 * FB + 2 * nh * FB + nh + nop + (2 * nh + 2 + 1) / 2 + 1;
+}
 
 #ifndef MWRT_ABS_MINB
 #define MWRT_ABS_MINB 4
-#endif
-#ifndef MWRT_ABS_PIPELINE
-#define MWRT_ABS_PIPELINE 0   // 1: prefetch the next H2O line's state (measured slower: registers)
 #endif
 template <int FB>
 __global__ void __launch_bounds__(kAbsThreads, MWRT_ABS_MINB)
@@ -172,37 +181,56 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
              const double* __restrict__ denice, const double* __restrict__ frq,
              double* __restrict__ awet, double* __restrict__ adry, double* __restrict__ aliq,
              double* __restrict__ aice, int* __restrict__ status) {
-  extern __shared__ double smem[];
+  extern __shared__ __align__(16) double smem[];
   const int nh = m.n_h2o, no = m.n_o2;
-  double* tab = smem;                     // n_table doubles: H2O columns then O2 columns
-  double* fblk = tab + m.n_table;         // FB frequencies of this block
-  double* dfm = fblk + FB;                // nh x FB: f_j - fl_i
+  const int nop = (no + 1) & ~1;          // O2 lines padded to an even count (dummy: strength 0)
+  double* hrow = smem;                    // nh x kHS
+  double* orow = hrow + nh * kHS;         // nop x kOS
+  double* fblk = orow + nop * kOS;        // FB frequencies of this block
+  double* fsq = fblk + FB;                // FB: f_j^2
+  double* dfm = fsq + FB;                 // nh x FB: f_j - fl_i   (slow paths keep the oracle's rounding)
   double* dfp = dfm + nh * FB;            // nh x FB: f_j + fl_i
-  double* ifl2 = dfp + nh * FB;           // nh: 1/fl_i^2
-  double* ifk2 = ifl2 + nh;               // no: 1/f_k^2
-  double* fsq = ifk2 + no;                // FB: f_j^2
-  double* dminh = fsq + FB;               // nh: min_j |f_j - fl_i|
-  double* dmino = dminh + nh;             // no: min_j |f_j - f_k|
-  int* hcls = reinterpret_cast<int*>(dmino + no);   // nh: H2O line class w.r.t. the 750 GHz cutoff
-  __shared__ double etab[64];               // exp_tb / log_tb tables (mwrt_common.cuh)
+  double* dminh = dfp + nh * FB;          // nh: min_j |f_j - fl_i|
+  double* dmino = dminh + nh;             // nop: min_j |f_j - f_k|
+  int* hcls = reinterpret_cast<int*>(dmino + nop);   // nh: H2O line class w.r.t. the 750 GHz cutoff
+  int* hord = hcls + nh;                  // nh: processing order, all-in lines first
+  int* cnt = hord + nh;                   // [0] all-in lines, [1] lines that contribute at all
+  __shared__ double etab[64];             // exp_tb / log_tb tables (mwrt_common.cuh)
   __shared__ __align__(16) double ltab[128];
   exp_tab_stage(etab);
   log_tab_stage(ltab);
   const int f0 = blockIdx.y * FB;
-  for (int i = threadIdx.x; i < m.n_table; i += blockDim.x) tab[i] = m.tables[i];
+  for (int i = threadIdx.x; i < nh * kHS; i += blockDim.x) {
+    const int ln = i / kHS, c = i - ln * kHS;
+    double v = 0.0;
+    if (c < MWRT_H2O_NCOL) v = m.tables[c * nh + ln];
+    else if (c == kH_IFL2) { const double fl = m.tables[MWRT_H2O_FL * nh + ln]; v = 1.0 / (fl * fl); }
+    hrow[i] = v;
+  }
+  const double* OT = m.tables + MWRT_H2O_NCOL * nh;
+  for (int i = threadIdx.x; i < nop * kOS; i += blockDim.x) {
+    const int ln = i / kOS, c = i - ln * kOS;
+    const int src = ln < no ? ln : no - 1;
+    double v = 0.0;
+    if (c < MWRT_O2_NCOL) v = OT[c * no + src];
+    else if (c == kO_IFK2) { const double fk = OT[MWRT_O2_F * no + src]; v = 1.0 / (fk * fk); }
+    if (ln >= no && c == MWRT_O2_S300) v = 0.0;
+    orow[i] = v;
+  }
   if (threadIdx.x < FB) {
     int jf = f0 + threadIdx.x;
-    fblk[threadIdx.x] = frq[jf < F ? jf : F - 1];  // tail block: repeat the last frequency
+    const double f = frq[jf < F ? jf : F - 1];  // tail block: repeat the last frequency
+    fblk[threadIdx.x] = f;
+    fsq[threadIdx.x] = f * f;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < nh * FB; i += blockDim.x) {
-    double fl = tab[MWRT_H2O_FL * nh + i / FB], f = fblk[i % FB];
+    double fl = hrow[(i / FB) * kHS + MWRT_H2O_FL], f = fblk[i % FB];
     dfm[i] = f - fl;
     dfp[i] = f + fl;
   }
   for (int i = threadIdx.x; i < nh; i += blockDim.x) {
-    double fl = tab[MWRT_H2O_FL * nh + i];
-    ifl2[i] = 1.0 / (fl * fl);
+    double fl = hrow[i * kHS + MWRT_H2O_FL];
     double dmin = fabs(fblk[0] - fl), lo = fblk[0], hi = fblk[0];
     for (int j = 1; j < FB; ++j) {
       dmin = fmin(dmin, fabs(fblk[j] - fl));
@@ -210,6 +238,11 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
       hi = fmax(hi, fblk[j]);
     }
     dminh[i] = dmin;
+    // Per-CTA line classes w.r.t. the 750 GHz cutoff, decided from the table centre with a 1 GHz
+    // margin for the pressure shift:
+    //   kAllIn    both wings of every block frequency inside  -> fast pair form
+    //   kAllOut   both wings outside (e.g. 916 GHz below 166 GHz) -> contributes exactly 0: skipped
+    //   anything else (one wing out, or a cutoff crossing inside the block) -> exact per-wing loop
     const bool w0_in = (fl - lo < 749.0) && (hi - fl < 749.0);   // |f - fc| < 750 for every f
     int cls = kMixed;
     if (w0_in && fl + hi < 749.0) cls = kAllIn;
@@ -217,15 +250,22 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     else if (fl - hi > 751.0 || lo - fl > 751.0) cls = kAllOut;
     hcls[i] = cls;
   }
-  const double* O = tab + MWRT_H2O_NCOL * nh;
-  for (int i = threadIdx.x; i < no; i += blockDim.x) {
-    double fk = O[MWRT_O2_F * no + i];
-    ifk2[i] = 1.0 / (fk * fk);
+  for (int i = threadIdx.x; i < nop; i += blockDim.x) {
+    double fk = orow[i * kOS + MWRT_O2_F];
     double dmin = fabs(fblk[0] - fk);
     for (int j = 1; j < FB; ++j) dmin = fmin(dmin, fabs(fblk[j] - fk));
     dmino[i] = dmin;
   }
-  if (threadIdx.x < FB) fsq[threadIdx.x] = fblk[threadIdx.x] * fblk[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = 0;
+    for (int i = 0; i < nh; ++i)
+      if (hcls[i] == kAllIn) hord[n++] = i;
+    cnt[0] = n;
+    for (int i = 0; i < nh; ++i)
+      if (hcls[i] != kAllIn && hcls[i] != kAllOut) hord[n++] = i;
+    cnt[1] = n;
+  }
   __syncthreads();
 
   const long long ipt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -267,7 +307,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
 
   const long long obase = (pidx * F + f0) * (long long)L + lev;  // + j*L per frequency
   double acc[FB];
-  double tmp[FB];  // rare-path scratch (local memory, dynamically indexed)
+  double tmp[FB];  // slow-path scratch (local memory, dynamically indexed)
 
   // ------------------------------------------------------------------ H2O (abh2o)
   {
@@ -281,28 +321,27 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     const double ti = div_fast(m.h2o_reftline, t);
     const double tiln = log_tb(ti, ltab);
     const double omti = 1.0 - ti;
-    const double* H = tab;
     const bool sd_on = m.h2o_sd != 0;
 
-    auto hoist = [&](int i) {
+    // full line state from its table row R and its three exps (width, self width, strength)
+    auto line_state = [&](const double* R, double e_x, double e_xs, double e_s) {
       H2OLine h;
-      h.w = H[MWRT_H2O_W0 * nh + i] * pda * exp_tb_(H[MWRT_H2O_X * nh + i] * tiln) +
-            H[MWRT_H2O_W0S * nh + i] * pvap * exp_tb_(H[MWRT_H2O_XS * nh + i] * tiln);
+      h.w = R[MWRT_H2O_W0] * pda * e_x + R[MWRT_H2O_W0S] * pvap * e_xs;
       // ti^0 = 1 exactly: most lines have no shift exponent, skip their exp (warp-uniform branch)
-      double shf = H[MWRT_H2O_SH * nh + i] * pda * (1.0 - H[MWRT_H2O_AAIR * nh + i] * tiln);
-      double shs = H[MWRT_H2O_SHS * nh + i] * pvap * (1.0 - H[MWRT_H2O_ASELF * nh + i] * tiln);
-      const double xh = H[MWRT_H2O_XH * nh + i], xhs = H[MWRT_H2O_XHS * nh + i];
+      double shf = R[MWRT_H2O_SH] * pda * (1.0 - R[MWRT_H2O_AAIR] * tiln);
+      double shs = R[MWRT_H2O_SHS] * pvap * (1.0 - R[MWRT_H2O_ASELF] * tiln);
+      const double xh = R[MWRT_H2O_XH], xhs = R[MWRT_H2O_XHS];
       if (xh != 0.0) shf *= exp_tb_(xh * tiln);
       if (xhs != 0.0) shs *= exp_tb_(xhs * tiln);
-      h.shift = H[MWRT_H2O_SR * nh + i] * h.w + shf + shs;
-      h.w2 = sd_on ? H[MWRT_H2O_W2 * nh + i] * pda + H[MWRT_H2O_W2S * nh + i] * pvap : 0.0;
-      h.dl2 = sd_on ? H[MWRT_H2O_D2 * nh + i] * pda + H[MWRT_H2O_D2S * nh + i] * pvap : 0.0;
+      h.shift = R[MWRT_H2O_SR] * h.w + shf + shs;
+      h.w2 = sd_on ? R[MWRT_H2O_W2] * pda + R[MWRT_H2O_W2S] * pvap : 0.0;
+      h.dl2 = sd_on ? R[MWRT_H2O_D2] * pda + R[MWRT_H2O_D2S] * pvap : 0.0;
       h.wsq = h.w * h.w;
       h.base = h.w * rcp_fast(562500.0 + h.wsq);
       // strength with (1/fl)^2 folded in; the common f^2 is applied once at the end
-      h.sp = H[MWRT_H2O_S1 * nh + i] * exp_tb_(fma(2.5, tiln, H[MWRT_H2O_B2 * nh + i] * omti)) * ifl2[i];
-      // fast pair form: sp*w*(D0+D1)/(D0 D1) = (n1*vv + n0) / (vv^2 + c4)
-      const double fc = H[MWRT_H2O_FL * nh + i] + h.shift;
+      h.sp = R[MWRT_H2O_S1] * e_s * R[kH_IFL2];
+      // fast form: sp*w*(D0+D1)/(D0 D1) = (n1*vv + n0) / (vv^2 + c4)
+      const double fc = R[MWRT_H2O_FL] + h.shift;
       const double fc2 = fc * fc;
       h.c3 = fc2 - h.wsq;
       h.c4 = 4.0 * fc2 * h.wsq;
@@ -310,94 +349,112 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
       h.n0 = h.n1 * (2.0 * fc2);
       return h;
     };
+    // does the fast form of this line need a correction at some frequency of the block?
+    auto needs_corr = [&](const H2OLine& g, int i, double fl) {
+      const double fc = fl + g.shift;
+      const bool sd_any = (g.w2 > 0.0) && (f_lo - fc < 10.0 * g.w) && (fc - f_hi < 10.0 * g.w);
+      const bool narrow = (g.w < 1e-3 * fl) && (dminh[i] - fabs(g.shift) < 1e-3 * fl);
+      return sd_any || narrow;
+    };
 
 #pragma unroll
     for (int j = 0; j < FB; ++j) acc[j] = 0.0;
     double basesum = 0.0;
-    auto hot = [&](int i) {
-      const H2OLine g = hoist(i);
-      return H2OHot{g.c3, g.c4, g.n1, g.n0, 2.0 * g.sp * g.base, g.w, g.shift, g.w2};
-    };
-    // Per-CTA line classes w.r.t. the 750 GHz cutoff (uniform branches, decided from the table
-    // centre with a 1 GHz margin for the pressure shift):
-    //   kAllIn    both wings of every block frequency inside  -> fast pair form
-    //   kAllOut   both wings outside (e.g. 916 GHz below 166 GHz) -> contributes exactly 0: skipped
-    //   kWing1Out f+fc always outside, f-fc always inside (e.g. 752 GHz) -> one Lorentzian per frequency
-    //   kMixed    anything else -> exact per-wing loop
-    for (int i = 0; i < nh; ++i) {
-      const int cls = hcls[i];
-      if (cls == kAllOut) continue;
-      const H2OHot h = hot(i);
-      const double fl = tab[MWRT_H2O_FL * nh + i];
-      const double fc = fl + h.shift;
-      const bool margin_ok = fabs(h.shift) < 1.0;
-      if (cls == kAllIn && margin_ok) {
-        // 7 FP64-pipe instructions per (line, frequency), see H2OLine
-        basesum += h.b2;
-#pragma unroll
-        for (int j = 0; j < FB; ++j) {
-          const double vv = fsq[j] - h.c3;
-          const double D = fma(vv, vv, h.c4);
-          const double num = fma(h.n1, vv, h.n0);
-          acc[j] = fma(num, rcp_fast(D), acc[j]);
-        }
-        // corrections: the speed-dependent shape near line centre, or a line that is both very
-        // narrow and very close to a frequency (exact per-wing form in the oracle's rounding order)
-        const bool sd_any = (h.w2 > 0.0) && (f_lo - fc < 10.0 * h.w) && (fc - f_hi < 10.0 * h.w);
-        const bool narrow = (h.w < 1e-3 * fl) && (dminh[i] - fabs(h.shift) < 1e-3 * fl);
-        if (sd_any || narrow) {
-          const H2OLine g = hoist(i);   // full line state, recomputed
-          const double* dm = dfm + i * FB;
-          const double* dp = dfp + i * FB;
+    const int n_in = cnt[0], n_act = cnt[1];
+    const int npairs = (n_in + 1) >> 1;
+    const int nitems = npairs + (n_act - n_in);
+    // work items: pairs of all-in lines (fast pair form + corrections), then the remaining lines one
+    // at a time through the exact per-wing loop
 #pragma unroll 1
+    for (int it = 0; it < nitems; ++it) {
+      int ia, ib, ma = kSlowNone, mb = kSlowNone;
+      if (it < npairs) {
+        const int q = 2 * it;
+        const bool has_b = q + 1 < n_in;
+        ia = hord[q];
+        ib = has_b ? hord[q + 1] : ia;
+        const double* Ra = hrow + ia * kHS;
+        const double* Rb = hrow + ib * kHS;
+        double ea[6], ev[6];
+        ea[0] = Ra[MWRT_H2O_X] * tiln;
+        ea[1] = Ra[MWRT_H2O_XS] * tiln;
+        ea[2] = fma(2.5, tiln, Ra[MWRT_H2O_B2] * omti);
+        ea[3] = Rb[MWRT_H2O_X] * tiln;
+        ea[4] = Rb[MWRT_H2O_XS] * tiln;
+        ea[5] = fma(2.5, tiln, Rb[MWRT_H2O_B2] * omti);
+        exp_tb_vec<6>(ea, ev, etab);   // six chains interleaved
+        const H2OLine ga = line_state(Ra, ev[0], ev[1], ev[2]);
+        const H2OLine gb = line_state(Rb, ev[3], ev[4], ev[5]);
+        const bool margin_ok = (fabs(ga.shift) < 1.0) && (fabs(gb.shift) < 1.0);
+        if (margin_ok) {
+          const double zb = has_b ? 1.0 : 0.0;   // odd count: the last pair's second line is a dummy
+          const PairHot h{ga.c3, ga.c4, ga.n1, ga.n0, gb.c3, gb.c4, gb.n1 * zb, gb.n0 * zb};
+          basesum += 2.0 * ga.sp * ga.base + (2.0 * gb.sp * gb.base) * zb;
+#pragma unroll
           for (int j = 0; j < FB; ++j) {
-            const double d0 = dm[j] - g.shift;
-            const double d1 = dp[j] + g.shift;
-            const bool use_sd = g.w2 > 0.0 && fabs(d0) < 10.0 * g.w;
-            if (!use_sd && !narrow) {   // this frequency keeps the fast form: no correction
-              tmp[j] = 0.0;
-              continue;
-            }
-            double ex;   // what the oracle adds for this line: sum over wings of (shape - base)
-            if (use_sd)
-              ex = sd_shape_re(g.w, g.w2, g.dl2, d0) - g.base;
-            else
-              ex = div_fast(g.w, fma(d0, d0, g.wsq)) - g.base;
-            ex += div_fast(g.w, fma(d1, d1, g.wsq)) - g.base;
-            // minus what the fast form contributed (recomputed bit-identically), base term included
-            const double vv = fsq[j] - g.c3;
-            const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
-            tmp[j] = fma(g.sp, ex + 2.0 * g.base, -fast);
+            const double u = fsq[j];
+            const double va = u - h.c3a, vb = u - h.c3b;
+            const double Da = fma(va, va, h.c4a), Db = fma(vb, vb, h.c4b);
+            const double na = fma(h.n1a, va, h.n0a), nb = fma(h.n1b, vb, h.n0b);
+            const double num = fma(nb, Da, na * Db);
+            acc[j] = fma(num, rcp_fast(Da * Db), acc[j]);
           }
-#pragma unroll
-          for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
-        }
-      } else if (cls == kWing1Out && margin_ok && !(h.w2 > 0.0)) {
-        // only the f - fc wing is inside the cutoff: sp * (w / (d0^2 + w^2) - base)
-        basesum += 0.5 * h.b2;
-        const double sw = 0.5 * h.n1, wsq = h.w * h.w;
-        const double* dm = dfm + i * FB;
-#pragma unroll
-        for (int j = 0; j < FB; ++j) {
-          const double d0 = dm[j] - h.shift;
-          acc[j] = fma(sw, rcp_fast(fma(d0, d0, wsq)), acc[j]);
+          ma = needs_corr(ga, ia, Ra[MWRT_H2O_FL]) ? kSlowCorr : kSlowNone;
+          mb = (has_b && needs_corr(gb, ib, Rb[MWRT_H2O_FL])) ? kSlowCorr : kSlowNone;
+        } else {   // a pressure shift of 1 GHz or more: never in the atmosphere, but stay exact
+          ma = kSlowExact;
+          mb = has_b ? kSlowExact : kSlowNone;
         }
       } else {
-        // exact per-wing evaluation with the cutoff tests (rare: a line within ~1 GHz of f +- 750)
-        const H2OLine g = hoist(i);
+        ia = ib = hord[n_in + (it - npairs)];
+        ma = kSlowExact;
+      }
+      // slow paths, one line at a time (single instantiation: this code is large and rarely hot):
+      //   kSlowExact  the oracle's per-wing evaluation with the 750 GHz cutoff tests
+      //   kSlowCorr   what the oracle adds minus what the fast form contributed, for the frequencies
+      //               where the speed-dependent shape applies or the line is narrow and very close
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {
+        const int mode = s ? mb : ma;
+        if (mode == kSlowNone) continue;
+        const int i = s ? ib : ia;
+        const double* R = hrow + i * kHS;
+        const H2OLine g = line_state(R, exp_tb_(R[MWRT_H2O_X] * tiln), exp_tb_(R[MWRT_H2O_XS] * tiln),
+                                     exp_tb_(fma(2.5, tiln, R[MWRT_H2O_B2] * omti)));
+        const double fl = R[MWRT_H2O_FL];
+        const bool narrow = (g.w < 1e-3 * fl) && (dminh[i] - fabs(g.shift) < 1e-3 * fl);
         const double* dm = dfm + i * FB;
         const double* dp = dfp + i * FB;
 #pragma unroll 1
         for (int j = 0; j < FB; ++j) {
           const double d0 = dm[j] - g.shift;
           const double d1 = dp[j] + g.shift;
-          double ex = 0.0;
-          if (g.w2 > 0.0 && fabs(d0) < 10.0 * g.w)
-            ex += sd_shape_re(g.w, g.w2, g.dl2, d0) - g.base;
-          else if (fabs(d0) < 750.0)
-            ex += div_fast(g.w, fma(d0, d0, g.wsq)) - g.base;
-          if (fabs(d1) < 750.0) ex += div_fast(g.w, fma(d1, d1, g.wsq)) - g.base;
-          tmp[j] = g.sp * ex;
+          const bool use_sd = g.w2 > 0.0 && fabs(d0) < 10.0 * g.w;
+          if (mode == kSlowExact) {
+            double ex = 0.0;
+            if (use_sd)
+              ex += sd_shape_re(g.w, g.w2, g.dl2, d0) - g.base;
+            else if (fabs(d0) < 750.0)
+              ex += div_fast(g.w, fma(d0, d0, g.wsq)) - g.base;
+            if (fabs(d1) < 750.0) ex += div_fast(g.w, fma(d1, d1, g.wsq)) - g.base;
+            tmp[j] = g.sp * ex;
+            continue;
+          }
+          if (!use_sd && !narrow) {   // this frequency keeps the fast form: no correction
+            tmp[j] = 0.0;
+            continue;
+          }
+          double ex;   // what the oracle adds for this line: sum over wings of (shape - base)
+          if (use_sd)
+            ex = sd_shape_re(g.w, g.w2, g.dl2, d0) - g.base;
+          else
+            ex = div_fast(g.w, fma(d0, d0, g.wsq)) - g.base;
+          ex += div_fast(g.w, fma(d1, d1, g.wsq)) - g.base;
+          // minus the fast form's contribution (base term included; equal to what the pair loop
+          // added up to the rounding of the pair merge)
+          const double vv = fsq[j] - g.c3;
+          const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
+          tmp[j] = fma(g.sp, ex + 2.0 * g.base, -fast);
         }
 #pragma unroll
         for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
@@ -430,15 +487,16 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     const bool dens118 = m.o2_dens118 != 0;
 
     auto hoist = [&](int k, double expv) {   // expv = exp(-be_k * th1)
+      const double* R = orow + k * kOS;
       O2Line o;
       const double wden = (dens118 && k == 0) ? dens : den;
-      o.df = O[MWRT_O2_W300 * no + k] * wden;
-      o.y = ymul * (O[MWRT_O2_Y0 * no + k] + O[MWRT_O2_Y1 * no + k] * th1);
-      o.gfac = 1.0 + pe2 * (O[MWRT_O2_G0 * no + k] + O[MWRT_O2_G1 * no + k] * th1);
-      o.fcen = O[MWRT_O2_F * no + k] + pe2 * (O[MWRT_O2_DNU0 * no + k] + O[MWRT_O2_DNU1 * no + k] * th1);
-      o.sp = O[MWRT_O2_S300 * no + k] * expv * ifk2[k];
+      o.df = R[MWRT_O2_W300] * wden;
+      o.y = ymul * (R[MWRT_O2_Y0] + R[MWRT_O2_Y1] * th1);
+      o.gfac = 1.0 + pe2 * (R[MWRT_O2_G0] + R[MWRT_O2_G1] * th1);
+      o.fcen = R[MWRT_O2_F] + pe2 * (R[MWRT_O2_DNU0] + R[MWRT_O2_DNU1] * th1);
+      o.sp = R[MWRT_O2_S300] * expv * R[kO_IFK2];
       o.df2 = o.df * o.df;
-      // fast pair form: sp*(sf1+sf2) = (n1*vv + n0)/(vv^2 + c4) with As = sp*df*g, P = sp*y*fc:
+      // fast form: sp*(sf1+sf2) = (n1*vv + n0)/(vv^2 + c4) with As = sp*df*g, P = sp*y*fc:
       //   n1 = 2 (As + P),  n0 = 4 (As fc^2 - P w^2)
       const double as = o.sp * (o.df * o.gfac);
       const double pp_ = (o.sp * o.y) * o.fcen;
@@ -452,59 +510,67 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
 
 #pragma unroll
     for (int j = 0; j < FB; ++j) acc[j] = 0.0;
-    auto hot = [&](int k, double expv) {
-      const O2Line g = hoist(k, expv);
-      return O2Hot{g.c3, g.c4, g.n1, g.n0, g.df, g.fcen};
-    };
-    // The line strengths need one exp each: a 17-deep serial chain.  They are evaluated G at a time,
-    // interleaved (exp_nb_vec), so the FP64 pipe sees G independent chains instead of one; the
-    // values are handed to the line loop by rotating a small register array (no dynamic indexing).
-    constexpr int G = 7;
-    for (int k0 = 0; k0 < no; k0 += G) {
+    // The line strengths need one exp each.  They are evaluated G at a time, interleaved
+    // (exp_tb_vec), so the FP64 pipe sees G independent chains; the values are handed to the pair
+    // loop by rotating a small register array (no dynamic indexing).
+    constexpr int G = 6;
+#pragma unroll 1
+    for (int k0 = 0; k0 < nop; k0 += G) {
       double ea[G], ev[G];
 #pragma unroll
-      for (int g = 0; g < G; ++g) ea[g] = -O[MWRT_O2_BE * no + (k0 + g < no ? k0 + g : no - 1)] * th1;
+      for (int g = 0; g < G; ++g)
+        ea[g] = -orow[(k0 + g < nop ? k0 + g : nop - 1) * kOS + MWRT_O2_BE] * th1;
       exp_tb_vec<G>(ea, ev, etab);
 #pragma unroll 1
-      for (int gi = 0; gi < G; ++gi) {
-      const int k = k0 + gi;
-      if (k >= no) break;
-      const double expv = ev[0];
+      for (int gi = 0; gi < G; gi += 2) {
+        const int k = k0 + gi;
+        if (k >= nop) break;
+        const double expa = ev[0], expb = ev[1];
 #pragma unroll
-      for (int q = 0; q + 1 < G; ++q) ev[q] = ev[q + 1];
-      const O2Hot o = hot(k, expv);
-      // sp*(sf1 + sf2) in the fast pair form: 7 FP64-pipe instructions per (line, frequency)
+        for (int q = 0; q + 2 < G; ++q) ev[q] = ev[q + 2];
+        const O2Line oa = hoist(k, expa);
+        const O2Line ob = hoist(k + 1, expb);
+        const PairHot h{oa.c3, oa.c4, oa.n1, oa.n0, ob.c3, ob.c4, ob.n1, ob.n0};
 #pragma unroll
-      for (int j = 0; j < FB; ++j) {
-        const double vv = fsq[j] - o.c3;
-        const double D = fma(vv, vv, o.c4);
-        const double num = fma(o.n1, vv, o.n0);
-        acc[j] = fma(num, rcp_fast(D), acc[j]);
-      }
-      // rare path: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency
-      const double fk = O[MWRT_O2_F * no + k];
-      const bool sd = m.o2_sd118 && k == 0 && (f_lo - o.fcen < 10.0 * o.df) && (o.fcen - f_hi < 10.0 * o.df);
-      const bool narrow = (o.df < 1e-3 * fk) && (dmino[k] - fabs(o.fcen - fk) < 1e-3 * fk);
-      if (sd || narrow) {
-        const O2Line g = hoist(k, expv);   // full line state, recomputed: this path is rare
-#pragma unroll 1
         for (int j = 0; j < FB; ++j) {
-          const double d1 = fblk[j] - g.fcen;
-          const double d2 = fblk[j] + g.fcen;
-          double sf1;
-          if (sd && fabs(d1) < 10.0 * g.df)
-            sf1 = o2_sd118_sf1(g.df, d1, g.y);
-          else
-            sf1 = div_fast(g.df * g.gfac + d1 * g.y, fma(d1, d1, g.df2));
-          const double sf2 = div_fast(g.df * g.gfac - d2 * g.y, fma(d2, d2, g.df2));
-          const double vv = fsq[j] - g.c3;
-          const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
-          tmp[j] = fma(g.sp, sf1 + sf2, -fast);
+          const double u = fsq[j];
+          const double va = u - h.c3a, vb = u - h.c3b;
+          const double Da = fma(va, va, h.c4a), Db = fma(vb, vb, h.c4b);
+          const double na = fma(h.n1a, va, h.n0a), nb = fma(h.n1b, vb, h.n0b);
+          const double num = fma(nb, Da, na * Db);
+          acc[j] = fma(num, rcp_fast(Da * Db), acc[j]);
         }
+        // rare: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency
+        const double fka = orow[k * kOS + MWRT_O2_F], fkb = orow[(k + 1) * kOS + MWRT_O2_F];
+        const bool sda = m.o2_sd118 && k == 0 && (f_lo - oa.fcen < 10.0 * oa.df) &&
+                         (oa.fcen - f_hi < 10.0 * oa.df);
+        const bool nwa = (oa.df < 1e-3 * fka) && (dmino[k] - fabs(oa.fcen - fka) < 1e-3 * fka);
+        const bool nwb = (ob.df < 1e-3 * fkb) && (dmino[k + 1] - fabs(ob.fcen - fkb) < 1e-3 * fkb);
+        const int ca = (sda || nwa) ? 1 : 0, cb = nwb ? 1 : 0;
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+          if (!(s ? cb : ca)) continue;
+          const int kk = k + s;
+          const bool sd = sda && s == 0;
+          const O2Line g = hoist(kk, s ? expb : expa);   // full line state, recomputed
+#pragma unroll 1
+          for (int j = 0; j < FB; ++j) {
+            const double d1 = fblk[j] - g.fcen;
+            const double d2 = fblk[j] + g.fcen;
+            double sf1;
+            if (sd && fabs(d1) < 10.0 * g.df)
+              sf1 = o2_sd118_sf1(g.df, d1, g.y);
+            else
+              sf1 = div_fast(g.df * g.gfac + d1 * g.y, fma(d1, d1, g.df2));
+            const double sf2 = div_fast(g.df * g.gfac - d2 * g.y, fma(d2, d2, g.df2));
+            const double vv = fsq[j] - g.c3;
+            const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
+            tmp[j] = fma(g.sp, sf1 + sf2, -fast);
+          }
 #pragma unroll
-        for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
-      }
-      }   // lines of the group
+          for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
+        }
+      }   // pairs of the group
     }     // groups
     const double scale = m.o2_abs_const * presda * (th * th * th);
     const double pdry_mb = pdrykpa * 10.0;
@@ -561,7 +627,7 @@ static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, c
                       double* adry, double* aliq, double* aice, int* status, cudaStream_t st) {
   const long long npts = (long long)P * L;
   dim3 grid((unsigned)((npts + kAbsThreads - 1) / kAbsThreads), (unsigned)((F + FB - 1) / FB));
-  size_t smem = sizeof(double) * (size_t)(m.n_table + 2 * FB + 2 * m.n_h2o * FB + 2 * (m.n_h2o + m.n_o2) + (m.n_h2o + 1) / 2 + 1);
+  size_t smem = sizeof(double) * (size_t)abs_smem_doubles(m.n_h2o, m.n_o2, FB);
   k_absorption<FB><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, p, tk, e, e_is_rh, e_out, rho_out,
                                                     denliq, denice, frq, awet, adry, aliq, aice,
                                                     status);
