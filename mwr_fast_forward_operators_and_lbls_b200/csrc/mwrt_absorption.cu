@@ -79,6 +79,12 @@ __device__ __forceinline__ cplx dcerror_f(double x, double y) {
   bs = cmul(bs, zh); bs.re += b0;
   return cdiv_f(as, bs);
 }
+__device__ __forceinline__ double sd_shape_re_inl(double width0, double width2, double delta2, double df) {
+  const cplx cden = cmake(width2, -delta2);
+  const cplx xrt = csqrt_f(cdiv_f(cmake(width0 - 1.5 * width2, df + 1.5 * delta2), cden));
+  const cplx pxw = cscale(cmul(xrt, dcerror_f(-xrt.im, xrt.re)), kSqrtPi);
+  return cdiv_f(cmake(2.0 * (1.0 - pxw.re), -2.0 * pxw.im), cden).re;
+}
 __device__ __noinline__ double sd_shape_re(double width0, double width2, double delta2, double df) {
   const cplx cden = cmake(width2, -delta2);
   const cplx xrt = csqrt_f(cdiv_f(cmake(width0 - 1.5 * width2, df + 1.5 * delta2), cden));
@@ -174,7 +180,7 @@ __host__ __device__ inline int abs_smem_doubles(int nh, int no, int FB) {
 #endif
 template <int FB>
 __global__ void __launch_bounds__(kAbsThreads, MWRT_ABS_MINB)
-k_absorption(const ModelDev m, const long long npts, const int L, const int F,
+k_absorption(const ModelDev m, const long long npts, const int L, const int F, const int nfb,
              const double* __restrict__ p_in, const double* __restrict__ tk_in,
              const double* __restrict__ e_in, const int e_is_rh, double* __restrict__ e_out,
              double* __restrict__ rho_out, const double* __restrict__ denliq,
@@ -199,7 +205,6 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
   __shared__ __align__(16) double ltab[128];
   exp_tab_stage(etab);
   log_tab_stage(ltab);
-  const int f0 = blockIdx.y * FB;
   for (int i = threadIdx.x; i < nh * kHS; i += blockDim.x) {
     const int ln = i / kHS, c = i - ln * kHS;
     double v = 0.0;
@@ -217,59 +222,74 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
     if (ln >= no && c == MWRT_O2_S300) v = 0.0;
     orow[i] = v;
   }
-  if (threadIdx.x < FB) {
-    int jf = f0 + threadIdx.x;
-    const double f = frq[jf < F ? jf : F - 1];  // tail block: repeat the last frequency
-    fblk[threadIdx.x] = f;
-    fsq[threadIdx.x] = f * f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < nh * FB; i += blockDim.x) {
-    double fl = hrow[(i / FB) * kHS + MWRT_H2O_FL], f = fblk[i % FB];
-    dfm[i] = f - fl;
-    dfp[i] = f + fl;
-  }
-  for (int i = threadIdx.x; i < nh; i += blockDim.x) {
-    double fl = hrow[i * kHS + MWRT_H2O_FL];
-    double dmin = fabs(fblk[0] - fl), lo = fblk[0], hi = fblk[0];
-    for (int j = 1; j < FB; ++j) {
-      dmin = fmin(dmin, fabs(fblk[j] - fl));
-      lo = fmin(lo, fblk[j]);
-      hi = fmax(hi, fblk[j]);
+  // Work items = (frequency block, tile of kAbsThreads points); CTA b owns the contiguous item range
+  // [items*b/G, items*(b+1)/G) -- normally exactly one item (see launch_abs).
+  const long long ntiles = (npts + kAbsThreads - 1) / kAbsThreads;
+  const long long nitems_all = ntiles * nfb;
+  const long long it_begin = nitems_all * blockIdx.x / gridDim.x;
+  const long long it_end = nitems_all * (blockIdx.x + 1) / gridDim.x;
+  int cur_fb = -1;
+#pragma unroll 1
+  for (long long item = it_begin; item < it_end; ++item) {
+  const int fb = (int)(item / ntiles);
+  const long long tile = item - (long long)fb * ntiles;
+  const int f0 = fb * FB;
+  if (fb != cur_fb) {
+    cur_fb = fb;
+    __syncthreads();   // everyone is done with the previous block's scratch (and with the tables' staging)
+    if (threadIdx.x < FB) {
+      int jf = f0 + threadIdx.x;
+      const double f = frq[jf < F ? jf : F - 1];  // tail block: repeat the last frequency
+      fblk[threadIdx.x] = f;
+      fsq[threadIdx.x] = f * f;
     }
-    dminh[i] = dmin;
-    // Per-CTA line classes w.r.t. the 750 GHz cutoff, decided from the table centre with a 1 GHz
-    // margin for the pressure shift:
-    //   kAllIn    both wings of every block frequency inside  -> fast pair form
-    //   kAllOut   both wings outside (e.g. 916 GHz below 166 GHz) -> contributes exactly 0: skipped
-    //   anything else (one wing out, or a cutoff crossing inside the block) -> exact per-wing loop
-    const bool w0_in = (fl - lo < 749.0) && (hi - fl < 749.0);   // |f - fc| < 750 for every f
-    int cls = kMixed;
-    if (w0_in && fl + hi < 749.0) cls = kAllIn;
-    else if (w0_in && fl + lo > 751.0) cls = kWing1Out;
-    else if (fl - hi > 751.0 || lo - fl > 751.0) cls = kAllOut;
-    hcls[i] = cls;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nh * FB; i += blockDim.x) {
+      double fl = hrow[(i / FB) * kHS + MWRT_H2O_FL], f = fblk[i % FB];
+      dfm[i] = f - fl;
+      dfp[i] = f + fl;
+    }
+    for (int i = threadIdx.x; i < nh; i += blockDim.x) {
+      double fl = hrow[i * kHS + MWRT_H2O_FL];
+      double dmin = fabs(fblk[0] - fl), lo = fblk[0], hi = fblk[0];
+      for (int j = 1; j < FB; ++j) {
+        dmin = fmin(dmin, fabs(fblk[j] - fl));
+        lo = fmin(lo, fblk[j]);
+        hi = fmax(hi, fblk[j]);
+      }
+      dminh[i] = dmin;
+      // Per-CTA line classes w.r.t. the 750 GHz cutoff, decided from the table centre with a 1 GHz
+      // margin for the pressure shift:
+      //   kAllIn    both wings of every block frequency inside  -> fast pair form
+      //   kAllOut   both wings outside (e.g. 916 GHz below 166 GHz) -> contributes exactly 0: skipped
+      //   anything else (one wing out, or a cutoff crossing inside the block) -> exact per-wing loop
+      const bool w0_in = (fl - lo < 749.0) && (hi - fl < 749.0);   // |f - fc| < 750 for every f
+      int cls = kMixed;
+      if (w0_in && fl + hi < 749.0) cls = kAllIn;
+      else if (w0_in && fl + lo > 751.0) cls = kWing1Out;
+      else if (fl - hi > 751.0 || lo - fl > 751.0) cls = kAllOut;
+      hcls[i] = cls;
+    }
+    for (int i = threadIdx.x; i < nop; i += blockDim.x) {
+      double fk = orow[i * kOS + MWRT_O2_F];
+      double dmin = fabs(fblk[0] - fk);
+      for (int j = 1; j < FB; ++j) dmin = fmin(dmin, fabs(fblk[j] - fk));
+      dmino[i] = dmin;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int n = 0;
+      for (int i = 0; i < nh; ++i)
+        if (hcls[i] == kAllIn) hord[n++] = i;
+      cnt[0] = n;
+      for (int i = 0; i < nh; ++i)
+        if (hcls[i] != kAllIn && hcls[i] != kAllOut) hord[n++] = i;
+      cnt[1] = n;
+    }
+    __syncthreads();
   }
-  for (int i = threadIdx.x; i < nop; i += blockDim.x) {
-    double fk = orow[i * kOS + MWRT_O2_F];
-    double dmin = fabs(fblk[0] - fk);
-    for (int j = 1; j < FB; ++j) dmin = fmin(dmin, fabs(fblk[j] - fk));
-    dmino[i] = dmin;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int n = 0;
-    for (int i = 0; i < nh; ++i)
-      if (hcls[i] == kAllIn) hord[n++] = i;
-    cnt[0] = n;
-    for (int i = 0; i < nh; ++i)
-      if (hcls[i] != kAllIn && hcls[i] != kAllOut) hord[n++] = i;
-    cnt[1] = n;
-  }
-  __syncthreads();
-
-  const long long ipt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (ipt >= npts) return;
+  const long long ipt = tile * kAbsThreads + threadIdx.x;
+  if (ipt < npts) {
   const long long pidx = ipt / L;
   const int lev = (int)(ipt - pidx * L);
 
@@ -280,7 +300,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
   const bool t_ok = (tk_raw > 50.0) && (tk_raw < 1000.0);
   const double tk = t_ok ? tk_raw : 300.0;
   double e_mb = e_in[ipt];
-  const bool first = (blockIdx.y == 0);
+  const bool first = (fb == 0);
   if (e_is_rh) e_mb = e_mb * goff_gratch_es(tk);
   const bool in_nan = isnan(p_mb) || isnan(tk_raw) || isnan(e_mb);
   const bool in_bad = in_nan || !t_ok;
@@ -408,8 +428,30 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
       } else {
         ia = ib = hord[n_in + (it - npairs)];
         ma = kSlowExact;
+        if (hcls[ia] == kWing1Out) {
+          // only the f - fc wing is inside the cutoff (e.g. 752 GHz): sp * (w / (d0^2 + w^2) - base)
+          const double* R = hrow + ia * kHS;
+          double ea[3], ev[3];
+          ea[0] = R[MWRT_H2O_X] * tiln;
+          ea[1] = R[MWRT_H2O_XS] * tiln;
+          ea[2] = fma(2.5, tiln, R[MWRT_H2O_B2] * omti);
+          exp_tb_vec<3>(ea, ev, etab);
+          const H2OLine g = line_state(R, ev[0], ev[1], ev[2]);
+          if (fabs(g.shift) < 1.0 && !(g.w2 > 0.0)) {
+            ma = kSlowNone;
+            basesum += g.sp * g.base;
+            const double sw = g.sp * g.w, sh = g.shift, wsq = g.wsq;
+            const double* dm = dfm + ia * FB;
+#pragma unroll
+            for (int j = 0; j < FB; ++j) {
+              const double d0 = dm[j] - sh;
+              acc[j] = fma(sw, rcp_fast(fma(d0, d0, wsq)), acc[j]);
+            }
+          }
+        }
       }
-      // slow paths, one line at a time (single instantiation: this code is large and rarely hot):
+      if ((ma | mb) == kSlowNone) continue;
+      // slow paths, one line at a time (single instantiation: this code is large):
       //   kSlowExact  the oracle's per-wing evaluation with the 750 GHz cutoff tests
       //   kSlowCorr   what the oracle adds minus what the fast form contributed, for the frequencies
       //               where the speed-dependent shape applies or the line is narrow and very close
@@ -419,12 +461,44 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
         if (mode == kSlowNone) continue;
         const int i = s ? ib : ia;
         const double* R = hrow + i * kHS;
-        const H2OLine g = line_state(R, exp_tb_(R[MWRT_H2O_X] * tiln), exp_tb_(R[MWRT_H2O_XS] * tiln),
-                                     exp_tb_(fma(2.5, tiln, R[MWRT_H2O_B2] * omti)));
+        double ea[3], ev[3];
+        ea[0] = R[MWRT_H2O_X] * tiln;
+        ea[1] = R[MWRT_H2O_XS] * tiln;
+        ea[2] = fma(2.5, tiln, R[MWRT_H2O_B2] * omti);
+        exp_tb_vec<3>(ea, ev, etab);
+        const H2OLine g = line_state(R, ev[0], ev[1], ev[2]);
         const double fl = R[MWRT_H2O_FL];
         const bool narrow = (g.w < 1e-3 * fl) && (dminh[i] - fabs(g.shift) < 1e-3 * fl);
         const double* dm = dfm + i * FB;
         const double* dp = dfp + i * FB;
+        if (mode == kSlowCorr && !narrow) {
+          // Speed-dependent shape only (22/183 GHz near their centres: every K-band channel in the
+          // lower troposphere, so this is not rare).  The line is not narrow, so the fast form
+          // equals the Lorentz pair to rounding and the correction is sp * (sd - lorentz) of the
+          // f - fc wing.  Two frequencies per step, both shapes inlined in one basic block so their
+          // long serial chains (complex sqrt, rational w(z)) interleave.
+          const double w10 = 10.0 * g.w;
+#pragma unroll 1
+          for (int j = 0; j < FB; j += 2) {
+            const int j1 = (j + 1 < FB) ? j + 1 : j;
+            const double da = dm[j] - g.shift, db = dm[j1] - g.shift;
+            const bool ua = fabs(da) < w10, ub = (fabs(db) < w10) && (j1 != j);
+            if (!(ua || ub)) continue;
+            const double sa = sd_shape_re_inl(g.w, g.w2, g.dl2, da);
+            const double sb = sd_shape_re_inl(g.w, g.w2, g.dl2, db);
+            const double la = g.w * rcp_fast(fma(da, da, g.wsq));
+            const double lb = g.w * rcp_fast(fma(db, db, g.wsq));
+            tmp[j] = ua ? g.sp * (sa - la) : 0.0;
+            if (j1 != j) tmp[j1] = ub ? g.sp * (sb - lb) : 0.0;
+          }
+          // frequencies skipped above must not add stale scratch
+#pragma unroll
+          for (int j = 0; j < FB; ++j) {
+            const double d0 = dm[j] - g.shift;
+            acc[j] += (fabs(d0) < w10) ? tmp[j] : 0.0;
+          }
+          continue;
+        }
 #pragma unroll 1
         for (int j = 0; j < FB; ++j) {
           const double d0 = dm[j] - g.shift;
@@ -547,6 +621,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
         const bool nwa = (oa.df < 1e-3 * fka) && (dmino[k] - fabs(oa.fcen - fka) < 1e-3 * fka);
         const bool nwb = (ob.df < 1e-3 * fkb) && (dmino[k + 1] - fabs(ob.fcen - fkb) < 1e-3 * fkb);
         const int ca = (sda || nwa) ? 1 : 0, cb = nwb ? 1 : 0;
+        if (!(ca | cb)) continue;
 #pragma unroll 1
         for (int s = 0; s < 2; ++s) {
           if (!(s ? cb : ca)) continue;
@@ -618,6 +693,8 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F,
       if (f0 + j < F) aice[obase + (long long)j * L] = a;
     }
   }
+  }   // ipt < npts
+  }   // work items
 }
 
 template <int FB>
@@ -626,9 +703,16 @@ static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, c
                       const double* denliq, const double* denice, const double* frq, double* awet,
                       double* adry, double* aliq, double* aice, int* status, cudaStream_t st) {
   const long long npts = (long long)P * L;
-  dim3 grid((unsigned)((npts + kAbsThreads - 1) / kAbsThreads), (unsigned)((F + FB - 1) / FB));
+  const int nfb = (F + FB - 1) / FB;
+  const long long items = ((npts + kAbsThreads - 1) / kAbsThreads) * nfb;
+  // One work item per CTA whenever the grid allows it.  Measured on B200 (config 2): a persistent grid
+  // (one resident wave looping over items) is 6-10 % SLOWER -- the per-CTA staging is LSU/ALU work that
+  // hides under other CTAs' FP64 work anyway, while a static split quantises to whole items per CTA
+  // and lets the warps of a CTA drift apart (more instruction-cache misses).  The item loop in the
+  // kernel only matters beyond 2^31-1 items.
+  const unsigned grid = (unsigned)(items < 0x7fffffffLL ? items : 0x7fffffffLL);
   size_t smem = sizeof(double) * (size_t)abs_smem_doubles(m.n_h2o, m.n_o2, FB);
-  k_absorption<FB><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, p, tk, e, e_is_rh, e_out, rho_out,
+  k_absorption<FB><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, nfb, p, tk, e, e_is_rh, e_out, rho_out,
                                                     denliq, denice, frq, awet, adry, aliq, aice,
                                                     status);
   MWRT_CUDA_OK(cudaGetLastError());
