@@ -217,6 +217,8 @@ int mwrt_measure_dfma_peak(double* flops_per_s, double* sm_clock_mhz_est);
 #define MWRT_MATH_LOG_NB 2
 #define MWRT_MATH_LOG_TB 3
 #define MWRT_MATH_RCP 4
+#define MWRT_MATH_RCP_SEED 5 /* raw MUFU.RCP64H */
+#define MWRT_MATH_RCP_NR1 6  /* seed + one quadratic Newton step */
 int mwrt_math_selftest_f64(int op, int64_t n, const double* x, double* y, void* stream);
 
 #ifdef __cplusplus

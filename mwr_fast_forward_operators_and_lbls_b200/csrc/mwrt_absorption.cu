@@ -146,8 +146,8 @@ __device__ __noinline__ double liq_abs_unit(int liq_model, double f, double tk) 
 // so a line's two wings are ONE fraction (n1*vv + n0)/(vv^2 + c4) per frequency, and two LINES a, b
 // share one reciprocal:  na/Da + nb/Db = (na Db + nb Da)/(Da Db):
 //   2 DADD (vv) + 2 DFMA (D) + 2 DFMA (n) + DMUL (Da Db) + DMUL, DFMA (numerator) + reciprocal
-//   (MUFU.RCP64H + 3 DFMA) + DFMA (accumulate) = 13 FP64-pipe instructions and 1 MUFU per
-//   (line pair, frequency), i.e. 6.5 per line instead of 7, with half the MUFU and f^2 loads.
+//   (MUFU.RCP64H + 2 DFMA, rcp_nr1) + DFMA (accumulate) = 12 FP64-pipe instructions and 1 MUFU per
+//   (line pair, frequency), i.e. 6 per line instead of 7, with half the MUFU and f^2 loads.
 // Rounding: the only cancellation is in vv (relative error ~ eps*f/(2*max(|f-fc|, w))); lines that are
 // both narrower than 1e-3*fc and closer than 1e-3*fc to a frequency of the block get the exact
 // per-wing form as a correction in the slow-path loop.
@@ -201,7 +201,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
   int* hcls = reinterpret_cast<int*>(dmino + nop);   // nh: H2O line class w.r.t. the 750 GHz cutoff
   int* hord = hcls + nh;                  // nh: processing order, all-in lines first
   int* cnt = hord + nh;                   // [0] all-in lines, [1] lines that contribute at all
-  __shared__ double etab[64];             // exp_tb / log_tb tables (mwrt_common.cuh)
+  __shared__ double etab[kExpTabN];             // exp_tb / log_tb tables (mwrt_common.cuh)
   __shared__ __align__(16) double ltab[128];
   exp_tab_stage(etab);
   log_tab_stage(ltab);
@@ -417,7 +417,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
             const double Da = fma(va, va, h.c4a), Db = fma(vb, vb, h.c4b);
             const double na = fma(h.n1a, va, h.n0a), nb = fma(h.n1b, vb, h.n0b);
             const double num = fma(nb, Da, na * Db);
-            acc[j] = fma(num, rcp_fast(Da * Db), acc[j]);
+            acc[j] = fma(num, rcp_nr1(Da * Db), acc[j]);
           }
           ma = needs_corr(ga, ia, Ra[MWRT_H2O_FL]) ? kSlowCorr : kSlowNone;
           mb = (has_b && needs_corr(gb, ib, Rb[MWRT_H2O_FL])) ? kSlowCorr : kSlowNone;
@@ -612,7 +612,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
           const double Da = fma(va, va, h.c4a), Db = fma(vb, vb, h.c4b);
           const double na = fma(h.n1a, va, h.n0a), nb = fma(h.n1b, vb, h.n0b);
           const double num = fma(nb, Da, na * Db);
-          acc[j] = fma(num, rcp_fast(Da * Db), acc[j]);
+          acc[j] = fma(num, rcp_nr1(Da * Db), acc[j]);
         }
         // rare: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency
         const double fka = orow[k * kOS + MWRT_O2_F], fkb = orow[(k + 1) * kOS + MWRT_O2_F];

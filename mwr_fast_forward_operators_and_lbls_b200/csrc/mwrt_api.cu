@@ -616,7 +616,7 @@ int mwrt_assemble_levels_f64(int S, int M, int K, int n_levels, double min_p, co
 }
 
 int mwrt_math_selftest_f64(int op, int64_t n, const double* x, double* y, void* stream) {
-  if (n <= 0 || !x || !y || op < 0 || op > MWRT_MATH_RCP)
+  if (n <= 0 || !x || !y || op < 0 || op > MWRT_MATH_RCP_NR1)
     return fail_arg(MWRT_E_ARG, "mwrt_math_selftest_f64: bad argument");
   return math_selftest_launch(op, n, x, y, (cudaStream_t)stream);
 }

@@ -77,8 +77,8 @@ int dfma_peak(double* flops, double* mhz) {
 // Elementwise evaluation of the device math helpers, for the unit tests (tests/test_gpu_parity.py).
 __global__ void k_math_selftest(const int op, const long long n, const double* __restrict__ x,
                                 double* __restrict__ y) {
-  __shared__ double etab[64];
-  __shared__ double ltab[2 * 64];
+  __shared__ double etab[kExpTabN];
+  __shared__ __align__(16) double ltab[2 * 64];
   exp_tab_stage(etab);
   log_tab_stage(ltab);
   __syncthreads();
@@ -92,6 +92,8 @@ __global__ void k_math_selftest(const int op, const long long n, const double* _
     case MWRT_MATH_LOG_NB: r = log_nb(v); break;
     case MWRT_MATH_LOG_TB: r = log_tb(v, ltab); break;
     case MWRT_MATH_RCP: r = rcp_fast(v); break;
+    case MWRT_MATH_RCP_SEED: r = rcp_seed(v); break;
+    case MWRT_MATH_RCP_NR1: r = rcp_nr1(v); break;
     default: r = nan("");
   }
   y[i] = r;

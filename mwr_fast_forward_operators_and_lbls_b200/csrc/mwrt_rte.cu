@@ -73,7 +73,7 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
       double* __restrict__ tmr, double* __restrict__ tauwet, double* __restrict__ taudry,
       double* __restrict__ tauliq, double* __restrict__ tauice, double* __restrict__ tau_layer,
       const int tl_angle, int* __restrict__ status) {
-  __shared__ double etab[64];        // exp_tb / log_tb tables (mwrt_common.cuh)
+  __shared__ double etab[kExpTabN];        // exp_tb / log_tb tables (mwrt_common.cuh)
   __shared__ __align__(16) double ltab[128];
   exp_tab_stage(etab);
   log_tab_stage(ltab);
@@ -216,7 +216,7 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     exp_tb_vec<NA>(ntau, ex, etab);
 #pragma unroll
     for (int a = 0; a < NA; ++a) den[a] = 1.0 + ex[a];
-    rcp_fast_vec<NA>(den, rden);
+    rcp_nr1_vec<NA>(den, rden);
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
       const double boftlay = fma(bfar, ex[a], bnear) * rden[a];

@@ -294,7 +294,7 @@ def measure_dfma_peak():
     return fl.value, mhz.value
 
 
-MATH_OPS = {"exp_nb": 0, "exp_tb": 1, "log_nb": 2, "log_tb": 3, "rcp": 4}
+MATH_OPS = {"exp_nb": 0, "exp_tb": 1, "log_nb": 2, "log_tb": 3, "rcp": 4, "rcp_seed": 5, "rcp_nr1": 6}
 
 
 def math_selftest(op, x):
