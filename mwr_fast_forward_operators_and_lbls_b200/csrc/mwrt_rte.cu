@@ -12,6 +12,7 @@
 // NA-way instruction-level parallelism.  One exp per (layer, angle): the transmission to the observer
 // is carried as a running product instead of PyRTlib's second exp(-tauprof).
 #include "mwrt_common.cuh"
+#include <type_traits>
 
 namespace mwrt {
 
@@ -55,20 +56,30 @@ __device__ __forceinline__ double bright_nb(double hvk, double b, const double* 
   return pos ? t : (isnan(b) ? b : 0.0);
 }
 
+// layer_mean for two strictly positive endpoints (the common case): same operations, no selects
+// beyond the |x1-x0| < 1e-9 rule
+__device__ __forceinline__ double layer_mean_pos(double x0, double x1, const double* __restrict__ ltab) {
+  const double dx = x1 - x0;
+  const double lm = dx * rcp_fast(log_tb(x1 * rcp_fast(x0), ltab));
+  return (fabs(dx) < 1e-09) ? x1 : lm;
+}
+
 // PLANE = plane-parallel path: ds(a, layer) = dz(layer) * amass(a) is formed in registers from z and
 // a per-angle air-mass table (no ds array, no slant-path kernel); otherwise ds is read from (P,A,L).
+// FROM_SAT (upwelling, levels walked top-down) is a template parameter so the lower/upper level of a
+// layer is chosen at compile time instead of by per-layer selects.
 // measured on B200 (profiles/r01b_*): the plane-parallel variant is fastest capped at 128 registers
 // (4 CTAs/SM); the general variant spills there and runs best uncapped
-template <int NA, bool CLOUDY, bool PLANE>
 #ifndef MWRT_RTE_MINB
 #define MWRT_RTE_MINB 3
 #endif
+template <int NA, bool CLOUDY, bool PLANE, bool FROM_SAT>
 __global__ void __launch_bounds__(kRteThreads, (PLANE && !CLOUDY) ? MWRT_RTE_MINB : 1)
 k_rte(const int P, const int L, const int F, const int A, const double* __restrict__ tk,
       const double* __restrict__ awet, const double* __restrict__ adry,
       const double* __restrict__ aliq, const double* __restrict__ aice,
       const double* __restrict__ ds, const double* __restrict__ z,
-      const double* __restrict__ amass_tab, const double* __restrict__ frq, const int from_sat,
+      const double* __restrict__ amass_tab, const double* __restrict__ frq,
       const double emis, double* __restrict__ tbtotal, double* __restrict__ tbatm,
       double* __restrict__ tmr, double* __restrict__ tauwet, double* __restrict__ taudry,
       double* __restrict__ tauliq, double* __restrict__ tauice, double* __restrict__ tau_layer,
@@ -117,11 +128,13 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
   for (int a = 0; a < NA; ++a)
     if (a0 + a == tl_angle) tl_amass = amass[a];
 
-  bool neg = false, anynan = false;
+  bool neg = false;
+  double tsum = 0.0;       // NaN detector for the temperatures (NaN in absorption or geometry shows
+                           // up in tauprof): checked once after the loop instead of per layer
   const bool want_tl = (tau_layer != nullptr) && (tl_angle >= a0) && (tl_angle < a0 + NA);
   if (want_tl) tau_layer[row] = 0.0;
-  const int dir = from_sat ? -1 : 1;
-  const int lev0 = from_sat ? L - 1 : 0;   // level sequence starts at the observer's end
+  constexpr int dir = FROM_SAT ? -1 : 1;
+  const int lev0 = FROM_SAT ? L - 1 : 0;   // level sequence starts at the observer's end
   const double zref = PLANE ? zp[0] : 0.0;
 
   // Software pipeline over the level sequence lev0, lev0+dir, ...:
@@ -140,13 +153,20 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     v.z = PLANE ? zp[lv] - zref : 0.0;
     return v;
   };
-  auto prep = [&](const Lvl& nr, const Lvl& fr, bool& ng, bool& nn) {
+  // GENERIC = false: wet and dry absorption strictly positive at both levels (decided by the caller)
+  auto prep = [&](auto generic, const Lvl& nr, const Lvl& fr, bool& ng) {
+    constexpr bool GENERIC = decltype(generic)::value;
     // nr = level nearer to the observer, fr = farther; lower/upper depends on the direction
-    const Lvl& lo = from_sat ? fr : nr;
-    const Lvl& up = from_sat ? nr : fr;
+    const Lvl& lo = FROM_SAT ? fr : nr;
+    const Lvl& up = FROM_SAT ? nr : fr;
     Lay y;
-    y.xw = layer_mean(lo.w, up.w, true, ng, ltab);
-    y.xd = layer_mean(lo.d, up.d, true, ng, ltab);
+    if (GENERIC) {
+      y.xw = layer_mean(lo.w, up.w, true, ng, ltab);
+      y.xd = layer_mean(lo.d, up.d, true, ng, ltab);
+    } else {
+      y.xw = layer_mean_pos(lo.w, up.w, ltab);
+      y.xd = layer_mean_pos(lo.d, up.d, ltab);
+    }
     y.xtot = y.xw + y.xd;
     y.xl = 0.0;
     y.xi = 0.0;
@@ -157,27 +177,30 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     }
     y.bfar = planck_mod(hvk, fr.t, etab);
     y.dz = up.z - lo.z;
-    nn = nn || isnan(y.xtot) || isnan(fr.t) || isnan(y.dz);
     return y;
+  };
+  auto all_pos = [](const Lvl& a, const Lvl& b) {
+    return (a.w > 0.0) && (b.w > 0.0) && (a.d > 0.0) && (b.d > 0.0);
   };
 
   Lvl lvA = load(lev0);
-  anynan = isnan(lvA.t);
+  tsum = lvA.t;
   double bnear = planck_mod(hvk, lvA.t, etab);
   Lvl lvB = load(lev0 + dir);
-  Lay cur = prep(lvA, lvB, neg, anynan);
+  Lay cur = prep(std::true_type{}, lvA, lvB, neg);
   lvA = lvB;
   lvB = load(L > 2 ? lev0 + 2 * dir : lev0 + dir);
 
-  for (int step = 1; step < L; ++step) {
+  // one step: the NA-angle stage of the current layer + the scalars of the next one
+  auto step_body = [&](auto generic, const int step) {
     const int clev = lev0 + step * dir;          // level reached in this step
-    const int j = from_sat ? clev + 1 : clev;    // layer index (upper level of the layer)
+    const int j = FROM_SAT ? clev + 1 : clev;    // layer index (upper level of the layer)
     // next layer's scalars (discarded after the last step) + prefetch of the level after it
-    bool ng2 = false, nn2 = false;
-    const Lay nxt = prep(lvA, lvB, ng2, nn2);
+    bool ng2 = false;
+    const Lay nxt = prep(generic, lvA, lvB, ng2);
     const bool more = step + 1 < L;
     neg = neg || (more && ng2);
-    anynan = anynan || (more && nn2);
+    tsum += lvA.t;
     lvA = lvB;
     lvB = load(step + 2 < L ? lev0 + (step + 2) * dir : clev);
 
@@ -189,11 +212,11 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
       if (CLOUDY) { sl[0] = fma(xl, dz, sl[0]); si[0] = fma(xi, dz, si[0]); }
       tauprof[0] = fma(xtot, dz, tauprof[0]);
     }
-    // per-angle work, written stage by stage over the NA angles (see exp_nb_vec)
+    // per-angle work, written stage by stage over the NA angles (see exp_tb_vec)
     double tau[NA], ntau[NA], ex[NA], den[NA], rden[NA];
     if (PLANE) {
       const double t0 = xtot * dz;                 // zenith optical depth of the layer
-      const double t0n = -fmin(t0, tcap);          // NaN is caught by `anynan`
+      const double t0n = -fmin(t0, tcap);          // NaN is caught through tauprof after the loop
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         ntau[a] = t0n * amass[a];
@@ -219,9 +242,11 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     rcp_nr1_vec<NA>(den, rden);
 #pragma unroll
     for (int a = 0; a < NA; ++a) {
+      // B(layer) * (trans_before - trans_after): the weight (1 - e^-tau) e^-tau_above of RTEquation.planck
       const double boftlay = fma(bfar, ex[a], bnear) * rden[a];
-      batm[a] = fma(boftlay * trans[a], 1.0 - ex[a], batm[a]);
-      trans[a] *= ex[a];
+      const double tn = trans[a] * ex[a];
+      batm[a] = fma(boftlay, trans[a] - tn, batm[a]);
+      trans[a] = tn;
     }
     if (want_tl && !PLANE) {
       double tl = 0.0;
@@ -232,13 +257,34 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     }
     bnear = bfar;
     cur = nxt;
+  };
+
+  // the two copies of the body differ only in how the next layer's means are formed; keeping each a
+  // single basic block lets the serial log/exp chains overlap the NA-angle stage.  Unrolling by two
+  // removes the register rotation of the pipeline (cur <- nxt, A <- B) in the plane-parallel kernel;
+  // the general kernel is larger and measured slower unrolled (instruction cache).
+  if (PLANE) {
+#pragma unroll 2
+    for (int step = 1; step < L; ++step) {
+      if (all_pos(lvA, lvB)) step_body(std::false_type{}, step);
+      else step_body(std::true_type{}, step);
+    }
+  } else {
+#pragma unroll 1
+    for (int step = 1; step < L; ++step) {
+      if (all_pos(lvA, lvB)) step_body(std::false_type{}, step);
+      else step_body(std::true_type{}, step);
+    }
   }
 
+  bool anynan = isnan(tsum);
+#pragma unroll
+  for (int a = 0; a < NS; ++a) anynan = anynan || isnan(tauprof[a]);
   const bool flagged = status && (status[p] & (MWRT_ST_NAN_INPUT | MWRT_ST_RANGE));  // earlier kernels
   const bool bad = neg || anynan || flagged;
   if (status && neg) atomicOr(&status[p], MWRT_ST_NEG_ABS);
   if (status && anynan && !neg && !flagged && jf == 0 && a0 == 0) atomicOr(&status[p], MWRT_ST_NAN_INPUT);
-  const double bbg = from_sat ? emis * planck_mod(hvk, tkp[0], etab) : planck_mod(hvk, kTCosmic, etab);
+  const double bbg = FROM_SAT ? emis * planck_mod(hvk, tkp[0], etab) : planck_mod(hvk, kTCosmic, etab);
   const long long obase = idx * (long long)A + a0;
 #pragma unroll
   for (int a = 0; a < NA; ++a) {
@@ -277,12 +323,18 @@ static int launch_rte_na(bool cloudy, int P, int L, int F, int A, const double* 
                          cudaStream_t st) {
   const long long n = (long long)P * F;
   dim3 grid((unsigned)((n + kRteThreads - 1) / kRteThreads), (unsigned)((A + NA - 1) / NA));
-#define MWRT_K_ARGS P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, from_sat, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status
+#define MWRT_K_ARGS P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status
+#define MWRT_K_LAUNCH(C_, P_)                                                              \
+  do {                                                                                     \
+    if (from_sat) k_rte<NA, C_, P_, true><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);     \
+    else k_rte<NA, C_, P_, false><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);             \
+  } while (0)
   const bool plane = (ds == nullptr);
-  if (cloudy && plane) k_rte<NA, true, true><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);
-  else if (cloudy) k_rte<NA, true, false><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);
-  else if (plane) k_rte<NA, false, true><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);
-  else k_rte<NA, false, false><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);
+  if (cloudy && plane) MWRT_K_LAUNCH(true, true);
+  else if (cloudy) MWRT_K_LAUNCH(true, false);
+  else if (plane) MWRT_K_LAUNCH(false, true);
+  else MWRT_K_LAUNCH(false, false);
+#undef MWRT_K_LAUNCH
 #undef MWRT_K_ARGS
   MWRT_CUDA_OK(cudaGetLastError());
   return 0;
