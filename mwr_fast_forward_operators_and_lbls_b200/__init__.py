@@ -10,7 +10,7 @@ multi-backend dispatch, no CPU fallback.  See DESIGN.md.
 """
 from .models import implemented_models, get_model, load_descriptor, Model  # noqa: F401
 from .forward import (Plan, simulate, vapor, absorption, slant_path, rte, bandpass,  # noqa: F401
-                      measure_dfma_peak, FIELDS)
+                      measure_dfma_peak, pinned_fields, FIELDS)
 from .tb_spectrum import TbCloudRTE  # noqa: F401
 from .synth import synth_profiles, band_frequencies, dense_spectrum, HATPRO_FRQ, HATPRO_ELEV  # noqa: F401
 

@@ -11,6 +11,9 @@
 #include <vector>
 
 #include "mwrt_common.cuh"
+#include <stdio.h>
+#include <time.h>
+#include <stdlib.h>
 
 namespace mwrt {
 
@@ -70,6 +73,8 @@ struct mwrt_model {
   double* d_tables;
 };
 
+constexpr int kSlots = 4;   // workspace slots = compute streams of the host pipeline
+
 struct mwrt_plan {
   ModelDev model;
   int L, F, A, flags, chunk;
@@ -87,17 +92,22 @@ struct mwrt_plan {
     double* mono[7];  // monochromatic RTE outputs when band-pass is on
     cudaEvent_t ev_abs, ev_rte;
     bool used;
-  } ws[2];
+  } ws[kSlots];
   cudaStream_t s_aux;
   // host-path resources (lazily created)
+  // Device staging holds the WHOLE batch (inputs, outputs, status: 100 MB for 10^4 profiles), so
+  // neither copy engine ever waits for a buffer to be recycled; only the (P,F,L) tau_layer field,
+  // which can be tens of GB, is staged per chunk in two slots.
   bool host_ready;
   cudaStream_t s_h2d, s_comp, s_d2h;
-  cudaEvent_t ev_h2d[2], ev_comp[2], ev_d2h[2];
-  int hcap;
-  double* h_in[2][6];
-  double* h_out[2][7];
+  cudaStream_t s_cmp[kSlots];                 // s_cmp[0] = s_comp, s_cmp[1] = s_aux, others own
+  std::vector<cudaEvent_t> ev_h2d, ev_comp;   // one per chunk
+  cudaEvent_t ev_tl[2];                       // tau_layer slot copied back
+  int hcap, hcap_tl;
+  double* h_in;       // 6 x hcap x L, field-major
+  double* h_out;      // 7 x hcap x Fo x A, field-major
   double* h_tl[2];
-  int* h_status[2];
+  int* h_status;
 };
 
 extern "C" {
@@ -232,7 +242,7 @@ int mwrt_bandpass_f64(int P, int C, int S, int A, const double* in, const double
 
 // ------------------------------------------------------------------------------------ plan
 static void plan_free_ws(mwrt_plan* pl) {
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < kSlots; ++k) {
     mwrt_plan::Slot& w = pl->ws[k];
     cudaFree(w.awet); cudaFree(w.adry); cudaFree(w.aliq); cudaFree(w.aice); cudaFree(w.ds); cudaFree(w.e);
     for (int i = 0; i < 7; ++i) cudaFree(w.mono[i]);
@@ -315,16 +325,24 @@ int mwrt_plan_create(const mwrt_model* m, int L, int F, int A, const double* frq
 
 static void plan_free_host(mwrt_plan* pl) {
   if (!pl->host_ready) return;
+  cudaFree(pl->h_in);
+  cudaFree(pl->h_out);
+  cudaFree(pl->h_status);
   for (int s = 0; s < 2; ++s) {
-    for (int i = 0; i < 6; ++i) cudaFree(pl->h_in[s][i]);
-    for (int i = 0; i < 7; ++i) cudaFree(pl->h_out[s][i]);
     cudaFree(pl->h_tl[s]);
-    cudaFree(pl->h_status[s]);
-    cudaEventDestroy(pl->ev_h2d[s]); cudaEventDestroy(pl->ev_comp[s]); cudaEventDestroy(pl->ev_d2h[s]);
+    pl->h_tl[s] = nullptr;
+    cudaEventDestroy(pl->ev_tl[s]);
   }
+  for (cudaEvent_t e : pl->ev_h2d) cudaEventDestroy(e);
+  for (cudaEvent_t e : pl->ev_comp) cudaEventDestroy(e);
+  pl->ev_h2d.clear();
+  pl->ev_comp.clear();
   cudaStreamDestroy(pl->s_h2d); cudaStreamDestroy(pl->s_comp); cudaStreamDestroy(pl->s_d2h);
+  for (int k = 2; k < kSlots; ++k) cudaStreamDestroy(pl->s_cmp[k]);
+  pl->h_in = pl->h_out = nullptr;
+  pl->h_status = nullptr;
   pl->host_ready = false;
-  pl->hcap = 0;
+  pl->hcap = pl->hcap_tl = 0;
 }
 
 int mwrt_plan_destroy(mwrt_plan* pl) {
@@ -484,104 +502,212 @@ int mwrt_plan_forward_device(mwrt_plan* pl, int P, const mwrt_profiles* in, cons
   return 0;
 }
 
-static int plan_host_init(mwrt_plan* pl, int hcap) {
-  if (pl->host_ready && hcap <= pl->hcap) return 0;
-  plan_free_host(pl);
-  MWRT_CUDA_OK(cudaStreamCreateWithFlags(&pl->s_h2d, cudaStreamNonBlocking));
-  MWRT_CUDA_OK(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
-  MWRT_CUDA_OK(cudaStreamCreateWithFlags(&pl->s_d2h, cudaStreamNonBlocking));
-  const int Fo = pl->C > 0 ? pl->C : pl->F;
-  for (int s = 0; s < 2; ++s) {
-    MWRT_CUDA_OK(cudaEventCreateWithFlags(&pl->ev_h2d[s], cudaEventDisableTiming));
-    MWRT_CUDA_OK(cudaEventCreateWithFlags(&pl->ev_comp[s], cudaEventDisableTiming));
-    MWRT_CUDA_OK(cudaEventCreateWithFlags(&pl->ev_d2h[s], cudaEventDisableTiming));
-    const int nin = (pl->flags & MWRT_F_CLOUDY) ? 6 : 4;
-    for (int i = 0; i < nin; ++i)
-      MWRT_CUDA_OK(cudaMalloc(&pl->h_in[s][i], sizeof(double) * (size_t)hcap * pl->L));
-    for (int i = 0; i < 7; ++i)
-      MWRT_CUDA_OK(cudaMalloc(&pl->h_out[s][i], sizeof(double) * (size_t)hcap * Fo * pl->A));
-    if (pl->flags & MWRT_F_TAU_LAYERS)
-      MWRT_CUDA_OK(cudaMalloc(&pl->h_tl[s], sizeof(double) * (size_t)hcap * pl->F * pl->L));
-    MWRT_CUDA_OK(cudaMalloc(&pl->h_status[s], sizeof(int) * (size_t)hcap));
+static int plan_host_init(mwrt_plan* pl, int hcap, int hcap_tl, int nchunks) {
+  const bool tl = pl->flags & MWRT_F_TAU_LAYERS;
+  if (!(pl->host_ready && hcap <= pl->hcap && (!tl || hcap_tl <= pl->hcap_tl))) {
+    plan_free_host(pl);
+    MWRT_CUDA_OK(cudaStreamCreateWithFlags(&pl->s_h2d, cudaStreamNonBlocking));
+    MWRT_CUDA_OK(cudaStreamCreateWithFlags(&pl->s_comp, cudaStreamNonBlocking));
+    MWRT_CUDA_OK(cudaStreamCreateWithFlags(&pl->s_d2h, cudaStreamNonBlocking));
+    pl->s_cmp[0] = pl->s_comp;
+    pl->s_cmp[1] = pl->s_aux;
+    for (int k = 2; k < kSlots; ++k) MWRT_CUDA_OK(cudaStreamCreateWithFlags(&pl->s_cmp[k], cudaStreamNonBlocking));
+    pl->host_ready = true;   // from here on plan_free_host releases what exists
+    const int Fo = pl->C > 0 ? pl->C : pl->F;
+    MWRT_CUDA_OK(cudaMalloc(&pl->h_in, sizeof(double) * 6 * (size_t)hcap * pl->L));
+    MWRT_CUDA_OK(cudaMalloc(&pl->h_out, sizeof(double) * 7 * (size_t)hcap * Fo * pl->A));
+    MWRT_CUDA_OK(cudaMalloc(&pl->h_status, sizeof(int) * (size_t)hcap));
+    for (int s = 0; s < 2; ++s) {
+      MWRT_CUDA_OK(cudaEventCreateWithFlags(&pl->ev_tl[s], cudaEventDisableTiming));
+      if (tl) MWRT_CUDA_OK(cudaMalloc(&pl->h_tl[s], sizeof(double) * (size_t)hcap_tl * pl->F * pl->L));
+    }
+    pl->hcap = hcap;
+    pl->hcap_tl = hcap_tl;
   }
-  pl->host_ready = true;
-  pl->hcap = hcap;
+  while ((int)pl->ev_h2d.size() < nchunks) {
+    cudaEvent_t a, b;
+    MWRT_CUDA_OK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    pl->ev_h2d.push_back(a);
+    MWRT_CUDA_OK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    pl->ev_comp.push_back(b);
+  }
   return 0;
+}
+
+// true when the non-null pointers of v[0..n) are equally spaced by `stride` bytes (so one 2-D copy
+// moves them all); k0/k1 = first/last non-null index, every index between must be non-null too
+static bool equally_spaced(const double* const* v, int n, int& k0, int& k1, ptrdiff_t& stride) {
+  k0 = -1; k1 = -1;
+  for (int i = 0; i < n; ++i)
+    if (v[i]) { if (k0 < 0) k0 = i; k1 = i; }
+  if (k0 < 0 || k1 == k0) return false;
+  stride = ((const char*)v[k1] - (const char*)v[k0]) / (k1 - k0);
+  if (stride <= 0) return false;
+  for (int i = k0; i <= k1; ++i)
+    if (!v[i] || (const char*)v[i] - (const char*)v[k0] != stride * (i - k0)) return false;
+  return true;
 }
 
 int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const mwrt_outputs* out) {
   int rc = check_io(pl, P, in, out, "mwrt_plan_forward_host: bad argument");
   if (rc) return rc;
-  // >= 4 chunks when the batch is large enough, so copies hide behind kernels
-  const int pieces = pl->split > 1 ? 2 * pl->split : 4;
-  int chunk = std::min(pl->chunk, std::max((P + pieces - 1) / pieces, 1024));
-  chunk = std::min(chunk, P);
-  rc = plan_reserve(pl, chunk, 2);
-  if (rc) return rc;
-  rc = plan_host_init(pl, chunk);
-  if (rc) return rc;
   const int L = pl->L, F = pl->F, A = pl->A;
   const int Fo = pl->C > 0 ? pl->C : F;
   const bool cloudy = pl->flags & MWRT_F_CLOUDY;
-  const double* hin[6] = {in->z, in->p, in->tk, in->rh, in->denliq, in->denice};
-  double* hout[7] = {out->tbtotal, out->tbatm, out->tmr, out->tauwet, out->taudry, out->tauliq, out->tauice};
-  // tapered schedule: half-size first and last chunks shorten the pipeline's fill (nothing to
-  // overlap the first kernels with) and drain (nothing overlaps the last D2H copy)
+  const bool want_tl = out->tau_layer != nullptr;
+  // Chunk schedule.  The step is bound by the device->host copy of the outputs (67 MB against 32 MB
+  // of inputs and ~1.2 ms of kernels for config 2), so the copy engine must start early and never
+  // idle.  Measured on B200 (tools/host_trace.py): equal chunks of ~1000 profiles on two alternating
+  // compute streams beat both fewer, larger chunks (late first copy, long drain) and a geometric
+  // ramp (tiny kernels are latency-bound: one kernel-3 thread walks all layers serially).
+  const int pieces = pl->split > 1 ? 2 * pl->split : 12;
+  int chunk = std::min(pl->chunk, std::max((P + pieces - 1) / pieces, 1024));
+  chunk = std::min(chunk, P);
   std::vector<int> sizes;
-  if (P >= 4 * chunk - 3 && chunk >= 2048) {
-    const int half = chunk / 2;
-    int left = P - 2 * half;
-    sizes.push_back(half);
-    while (left > 0) {
-      sizes.push_back(std::min(chunk, left));
-      left -= sizes.back();
-    }
-    sizes.push_back(half);
-  } else {
-    for (int left = P; left > 0; left -= sizes.back()) sizes.push_back(std::min(chunk, left));
+  for (int left = P; left > 0; left -= sizes.back()) sizes.push_back(std::min(chunk, left));
+  const int nchunks = (int)sizes.size();
+  static const int nstr = [] { const char* e = getenv("MWRT_HOST_STREAMS"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > kSlots ? kSlots : v); }();
+  rc = plan_reserve(pl, chunk, nstr);
+  if (rc) return rc;
+  rc = plan_host_init(pl, P, chunk, nchunks);
+  if (rc) return rc;
+  const size_t in_pitch = (size_t)pl->hcap * L, out_pitch = (size_t)pl->hcap * Fo * A;   // doubles
+  const double* hin[6] = {in->z, in->p, in->tk, in->rh, cloudy ? in->denliq : nullptr,
+                          cloudy ? in->denice : nullptr};
+  double* hout[7] = {out->tbtotal, out->tbatm, out->tmr, out->tauwet, out->taudry, out->tauliq, out->tauice};
+  // Clear sky: tauliq / tauice are identically zero (NaN for flagged profiles).  They are neither
+  // computed nor moved over PCIe (17 % of the output bytes each): the host fills them while the GPU
+  // works and patches the flagged profiles once the status words are back.
+  double* host_fill[2] = {nullptr, nullptr};
+  if (!cloudy) {
+    host_fill[0] = hout[5];
+    host_fill[1] = hout[6];
+    hout[5] = hout[6] = nullptr;
   }
+  const int nin = cloudy ? 6 : 4;
+  int ik0, ik1, ok0, ok1;
+  ptrdiff_t istride = 0, ostride = 0;
+  const bool in_2d = equally_spaced(hin, nin, ik0, ik1, istride) && ik0 == 0 && ik1 == nin - 1;
+  const bool out_2d = equally_spaced(const_cast<const double* const*>(hout), 7, ok0, ok1, ostride);
+
+  // MWRT_TRACE=1: timing events per chunk, timeline printed to stderr after the call (tuning aid)
+  static const bool trace = [] { const char* e = getenv("MWRT_TRACE"); return e && atoi(e) != 0; }();
+  std::vector<cudaEvent_t> tev;
+  cudaEvent_t tev0 = nullptr;
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tev.push_back(e);
+  };
+  timespec ts0, ts1;
+  if (trace) {
+    cudaEventCreate(&tev0);
+    cudaEventRecord(tev0, pl->s_h2d);
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+  }
+
+  // all inputs go up front, chunk by chunk, so the bus is free for results as early as possible
   int p0 = 0;
-  for (int c = 0; c < (int)sizes.size(); p0 += sizes[c], ++c) {
-    const int n = sizes[c];
-    const int s = c & 1;
-    // input slot s is free once the kernels of chunk c-2 have run
-    if (c >= 2) MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_h2d, pl->ev_comp[s], 0));
-    for (int i = 0; i < (cloudy ? 6 : 4); ++i)
-      MWRT_CUDA_OK(cudaMemcpyAsync(pl->h_in[s][i], hin[i] + (size_t)p0 * L, sizeof(double) * (size_t)n * L,
-                                   cudaMemcpyHostToDevice, pl->s_h2d));
-    MWRT_CUDA_OK(cudaEventRecord(pl->ev_h2d[s], pl->s_h2d));
-    MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_comp, pl->ev_h2d[s], 0));
-    // output slot s is free once chunk c-2 has been copied back
-    if (c >= 2) {
-      MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_comp, pl->ev_d2h[s], 0));
-      MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_aux, pl->ev_d2h[s], 0));
+  for (int c = 0; c < nchunks; p0 += sizes[c], ++c) {
+    const size_t off = (size_t)p0 * L, bytes = sizeof(double) * (size_t)sizes[c] * L;
+    if (in_2d) {
+      MWRT_CUDA_OK(cudaMemcpy2DAsync(pl->h_in + off, sizeof(double) * in_pitch, hin[0] + off, (size_t)istride,
+                                     bytes, nin, cudaMemcpyHostToDevice, pl->s_h2d));
+    } else {
+      for (int i = 0; i < nin; ++i)
+        MWRT_CUDA_OK(cudaMemcpyAsync(pl->h_in + i * in_pitch + off, hin[i] + off, bytes,
+                                     cudaMemcpyHostToDevice, pl->s_h2d));
     }
-    mwrt_profiles din = {pl->h_in[s][0], pl->h_in[s][1], pl->h_in[s][2], pl->h_in[s][3],
-                         cloudy ? pl->h_in[s][4] : nullptr, cloudy ? pl->h_in[s][5] : nullptr};
+    MWRT_CUDA_OK(cudaEventRecord(pl->ev_h2d[c], pl->s_h2d));
+    mark(pl->s_h2d);
+  }
+  p0 = 0;
+  for (int c = 0; c < nchunks; p0 += sizes[c], ++c) {
+    const int n = sizes[c];
+    const int s = c % nstr;
+    const int stl = c & 1;   // tau_layer staging slot
+    const size_t ioff = (size_t)p0 * L, ooff = (size_t)p0 * Fo * A;
+    // Chunk c runs kernel 1 then kernel 3 on compute stream c&1: neighbouring chunks are on different
+    // streams, so the tail of one chunk's kernels (partial last wave, the long serial walk of kernel
+    // 3) overlaps the next chunk's kernel 1, while chunks c and c-2 -- which share a workspace slot --
+    // are ordered by their stream.
+    cudaStream_t sc = pl->s_cmp[s];
+    MWRT_CUDA_OK(cudaStreamWaitEvent(sc, pl->ev_h2d[c], 0));
+    // the tau_layer slot is free once chunk c-2 has been copied back (kernel 3 writes it)
+    if (want_tl && c >= 2) MWRT_CUDA_OK(cudaStreamWaitEvent(sc, pl->ev_tl[stl], 0));
+    mwrt_profiles din = {pl->h_in + ioff, pl->h_in + in_pitch + ioff, pl->h_in + 2 * in_pitch + ioff,
+                         pl->h_in + 3 * in_pitch + ioff, cloudy ? pl->h_in + 4 * in_pitch + ioff : nullptr,
+                         cloudy ? pl->h_in + 5 * in_pitch + ioff : nullptr};
     mwrt_outputs dout;
     double** df[7] = {&dout.tbtotal, &dout.tbatm, &dout.tmr, &dout.tauwet, &dout.taudry, &dout.tauliq, &dout.tauice};
-    for (int i = 0; i < 7; ++i) *df[i] = hout[i] ? pl->h_out[s][i] : nullptr;
-    dout.tau_layer = out->tau_layer ? pl->h_tl[s] : nullptr;
-    dout.status = pl->h_status[s];
-    rc = forward_chunk(pl, s, n, din, dout, pl->s_comp, pl->s_aux);   // kernel 3 on the side stream
+    for (int i = 0; i < 7; ++i) *df[i] = hout[i] ? pl->h_out + i * out_pitch + ooff : nullptr;
+    dout.tau_layer = want_tl ? pl->h_tl[stl] : nullptr;
+    dout.status = pl->h_status + p0;
+    rc = forward_chunk(pl, s, n, din, dout, sc, sc);
     if (rc) return rc;
-    MWRT_CUDA_OK(cudaEventRecord(pl->ev_comp[s], pl->s_aux));
-    MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_d2h, pl->ev_comp[s], 0));
-    for (int i = 0; i < 7; ++i)
-      if (hout[i])
-        MWRT_CUDA_OK(cudaMemcpyAsync(hout[i] + (size_t)p0 * Fo * A, pl->h_out[s][i],
-                                     sizeof(double) * (size_t)n * Fo * A, cudaMemcpyDeviceToHost, pl->s_d2h));
-    if (out->tau_layer)
-      MWRT_CUDA_OK(cudaMemcpyAsync(out->tau_layer + (size_t)p0 * F * L, pl->h_tl[s],
+    mark(sc);
+    mark(sc);
+    MWRT_CUDA_OK(cudaEventRecord(pl->ev_comp[c], sc));
+    MWRT_CUDA_OK(cudaStreamWaitEvent(pl->s_d2h, pl->ev_comp[c], 0));
+    const size_t obytes = sizeof(double) * (size_t)n * Fo * A;
+    if (out_2d) {
+      MWRT_CUDA_OK(cudaMemcpy2DAsync(hout[ok0] + ooff, (size_t)ostride, pl->h_out + ok0 * out_pitch + ooff,
+                                     sizeof(double) * out_pitch, obytes, ok1 - ok0 + 1,
+                                     cudaMemcpyDeviceToHost, pl->s_d2h));
+    } else {
+      for (int i = 0; i < 7; ++i)
+        if (hout[i])
+          MWRT_CUDA_OK(cudaMemcpyAsync(hout[i] + ooff, pl->h_out + i * out_pitch + ooff, obytes,
+                                       cudaMemcpyDeviceToHost, pl->s_d2h));
+    }
+    if (want_tl) {
+      MWRT_CUDA_OK(cudaMemcpyAsync(out->tau_layer + (size_t)p0 * F * L, pl->h_tl[stl],
                                    sizeof(double) * (size_t)n * F * L, cudaMemcpyDeviceToHost, pl->s_d2h));
-    if (out->status)
-      MWRT_CUDA_OK(cudaMemcpyAsync(out->status + p0, pl->h_status[s], sizeof(int) * (size_t)n,
-                                   cudaMemcpyDeviceToHost, pl->s_d2h));
-    MWRT_CUDA_OK(cudaEventRecord(pl->ev_d2h[s], pl->s_d2h));
+      MWRT_CUDA_OK(cudaEventRecord(pl->ev_tl[stl], pl->s_d2h));
+    }
+    mark(pl->s_d2h);
   }
+  // status: one small copy at the end (kernel 3 of the last chunk has run once ev_comp fired)
+  if (out->status)
+    MWRT_CUDA_OK(cudaMemcpyAsync(out->status, pl->h_status, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost,
+                                 pl->s_d2h));
+  if (trace) clock_gettime(CLOCK_MONOTONIC, &ts1);
+  std::vector<int> st_local;
+  int* st_host = out->status;
+  if ((host_fill[0] || host_fill[1]) && !st_host) {   // the patch below needs the status words
+    st_local.resize(P);
+    st_host = st_local.data();
+    MWRT_CUDA_OK(cudaMemcpyAsync(st_host, pl->h_status, sizeof(int) * (size_t)P, cudaMemcpyDeviceToHost,
+                                 pl->s_d2h));
+  }
+  for (int k = 0; k < 2; ++k)
+    if (host_fill[k]) memset(host_fill[k], 0, sizeof(double) * (size_t)P * Fo * A);
   MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_d2h));
-  MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_aux));
-  MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_comp));
+  for (int k = 0; k < nstr; ++k) MWRT_CUDA_OK(cudaStreamSynchronize(pl->s_cmp[k]));
+  if (host_fill[0] || host_fill[1]) {
+    const size_t row = (size_t)Fo * A;
+    const double qnan = nan("");
+    for (int p = 0; p < P; ++p)
+      if (st_host[p] & (MWRT_ST_NAN_INPUT | MWRT_ST_RANGE | MWRT_ST_NEG_ABS))   // kernel 3's `bad`
+        for (int k = 0; k < 2; ++k)
+          if (host_fill[k])
+            for (size_t i = 0; i < row; ++i) host_fill[k][(size_t)p * row + i] = qnan;
+  }
+  if (trace) {
+    fprintf(stderr, "mwrt trace: all work queued after %.3f ms of host time\n",
+            (ts1.tv_sec - ts0.tv_sec) * 1e3 + (ts1.tv_nsec - ts0.tv_nsec) * 1e-6);
+    fprintf(stderr, "mwrt trace (ms since first H2D was queued): chunk size | h2d abs rte d2h done at\n");
+    for (int c = 0; c < nchunks; ++c) {
+      float t[4] = {0, 0, 0, 0};
+      cudaEventElapsedTime(&t[0], tev0, tev[c]);
+      for (int k = 1; k < 4; ++k) cudaEventElapsedTime(&t[k], tev0, tev[nchunks + 3 * c + k - 1]);
+      fprintf(stderr, "  %d %6d | %.3f %.3f %.3f %.3f\n", c, sizes[c], t[0], t[1], t[2], t[3]);
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    cudaEventDestroy(tev0);
+  }
   return 0;
 }
 

@@ -141,9 +141,9 @@ class Plan:
             if x.shape != (P, self.L):
                 raise ValueError("inputs must have shape (P,%d)" % self.L)
         res = out if out is not None else {}
-        for f in fields:
-            if f not in res:
-                res[f] = np.empty((P, self.Fo, self.A), dtype=np.float64)
+        missing = [f for f in fields if f not in res]
+        if missing:   # one pinned block: asynchronous copies, and one 2-D copy per chunk for all fields
+            res.update(pinned_fields(missing, (P, self.Fo, self.A)))
         if self.tau_layers and "tau_layer" not in res:
             res["tau_layer"] = np.empty((P, self.F, self.L), dtype=np.float64)
         if "status" not in res:
@@ -162,6 +162,17 @@ class Plan:
         _lib.check(self.lib.mwrt_plan_forward_host(self._h, int(P), C.byref(pin), C.byref(pout)),
                    "forward_host")
         return res
+
+
+def pinned_fields(names, shape, dtype=np.float64):
+    """dict name -> numpy view of ONE page-locked block (fields equally spaced): host buffers for
+    `Plan.forward_host` that the library moves with a single 2-D copy per chunk.  The block stays
+    alive as long as any view does."""
+    names = list(names)
+    block = torch.empty((len(names),) + tuple(shape), dtype=torch.from_numpy(np.empty(0, dtype)).dtype)
+    block = block.pin_memory()
+    arr = block.numpy()
+    return {n: arr[i] for i, n in enumerate(names)}
 
 
 def simulate(z, p, t, rh, frq, angles, model, ray_tracing=False, from_sat=False, denliq=None,

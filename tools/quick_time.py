@@ -47,8 +47,9 @@ for name, fn in (("absorption", t_abs), ("slant", t_ds), ("rte", t_rte)):
         e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     print("%-10s %.3f ms (min %.3f)" % (name, float(np.median(ts)), min(ts)))
 # host path
-hp = {k: torch.from_numpy(v).pin_memory() for k, v in d.items()}
-ho = {k: torch.empty((P, 14, 10), dtype=torch.float64).pin_memory().numpy() for k in pkg.FIELDS}
+hp = pkg.pinned_fields(list(d.keys()), d["z"].shape)
+for k in d: hp[k][...] = d[k]
+ho = pkg.pinned_fields(pkg.FIELDS, (P, 14, 10))
 ho["status"] = torch.empty((P,), dtype=torch.int32).pin_memory().numpy()
 for _ in range(3): plan.forward_host(hp["z"], hp["p"], hp["t"], hp["rh"], out=ho)
 ts = []

@@ -8,9 +8,10 @@ import mwr_fast_forward_operators_and_lbls_b200 as pkg
 P, L = 10000, 100
 d = pkg.synth_profiles(P, L, seed=1234)
 dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
-hp = {k: torch.from_numpy(v).pin_memory() for k, v in d.items()}
+hp = pkg.pinned_fields(list(d.keys()), d["z"].shape)
+for k in d: hp[k][...] = d[k]
 fields = ("tbtotal", "tbatm", "tmr", "tauwet", "taudry", "tauliq")
-ho = {k: torch.empty((P, 14, 10), dtype=torch.float64).pin_memory().numpy() for k in fields}
+ho = pkg.pinned_fields(fields, (P, 14, 10))
 ho["status"] = torch.empty((P,), dtype=torch.int32).pin_memory().numpy()
 ref = None
 for split in (1, 2, 3, 4, 6, 8):
