@@ -380,3 +380,39 @@ def test_device_math_helpers(pkg):
     assert np.max(np.abs(seed * x - 1.0)) < 2.0 ** -19.5
     nr1 = math_selftest("rcp_nr1", x).cpu().numpy()
     assert np.max(np.abs(nr1 * x - 1.0)) < 2e-12
+
+
+def test_host_entry_field_subsets_nan_patch_and_layouts(pkg):
+    """Host entry: (a) one pinned block (single 2-D copy per chunk) vs separately allocated arrays,
+    (b) a subset of fields, (c) clear sky: tauliq/tauice are filled on the host -- zero, NaN for the
+    flagged profile -- and must equal what the device entry writes, (d) cloudy plans move them."""
+    import torch
+    P, L = 3000, 30
+    d = pkg.synth_profiles(P, L, seed=16, clouds=True)
+    d["t"][1234, 7] = np.nan                                   # one flagged profile
+    plan = pkg.Plan("R24", L, pkg.HATPRO_FRQ, pkg.HATPRO_ELEV)
+    fields = pkg.FIELDS
+    dev = plan.forward(*(torch.from_numpy(d[k]).cuda() for k in ("z", "p", "t", "rh")), fields=fields)
+    torch.cuda.synchronize()
+    blk = plan.forward_host(d["z"], d["p"], d["t"], d["rh"], fields=fields)          # pinned block
+    sep = {f: np.empty((P, 14, 10)) for f in fields}                                 # pageable, separate
+    sep = plan.forward_host(d["z"], d["p"], d["t"], d["rh"], fields=fields, out=sep)
+    for k in fields + ("status",):
+        assert np.array_equal(cpu(dev[k]), blk[k], equal_nan=True), k
+        assert np.array_equal(cpu(dev[k]), sep[k], equal_nan=True), k
+    assert np.isnan(blk["tauliq"][1234]).all() and blk["status"][1234] != 0
+    assert (np.delete(blk["tauliq"], 1234, axis=0) == 0.0).all()
+    sub = plan.forward_host(d["z"], d["p"], d["t"], d["rh"], fields=("tbtotal", "tauliq"))
+    assert set(sub) == {"tbtotal", "tauliq", "status"}
+    assert np.array_equal(sub["tbtotal"], blk["tbtotal"], equal_nan=True)
+    assert np.array_equal(sub["tauliq"], blk["tauliq"], equal_nan=True)
+    # cloudy: liquid optical depth is computed and moved
+    cplan = pkg.Plan("R24", L, pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, cloudy=True)
+    zero = np.zeros_like(d["denliq"])
+    cdev = cplan.forward(*(torch.from_numpy(d[k]).cuda() for k in ("z", "p", "t", "rh")),
+                         denliq=torch.from_numpy(d["denliq"]).cuda(), denice=torch.from_numpy(zero).cuda())
+    torch.cuda.synchronize()
+    chost = cplan.forward_host(d["z"], d["p"], d["t"], d["rh"], denliq=d["denliq"], denice=zero)
+    for k in fields:
+        assert np.array_equal(cpu(cdev[k]), chost[k], equal_nan=True), k
+    assert np.nanmax(chost["tauliq"]) > 0.0
