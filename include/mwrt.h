@@ -154,6 +154,20 @@ int mwrt_plan_set_emissivity(mwrt_plan* plan, double es);
  * caller's stream still completes after everything.  The host entry point uses 2*pieces chunks.
  * Default 1 (no split). */
 int mwrt_plan_set_split(mwrt_plan* plan, int pieces);
+/* Multi-GPU gather fused into the result stores ("RTE epilogue writes through peer
+ * pointers").  The (P,F,A) result pointers handed to mwrt_plan_forward_device are then written
+ *   mode MWRT_OUT_PLAIN      as ordinary device memory (default);
+ *   mode MWRT_OUT_MULTICAST  with NVLink multicast stores: the pointers are MULTICAST addresses of a
+ *                            symmetric buffer, NVSwitch replicates each store to every rank;
+ *   mode MWRT_OUT_PEERS      once per peer: plain stores to pointer + peer_byte_offsets[r], r < npeer
+ *                            (<= MWRT_MAX_PEERS; include 0 for the own copy).
+ * status and tau_layer are always written plainly.  The caller orders the ranks (a barrier after the
+ * step) before anyone reads the gathered buffers. */
+#define MWRT_OUT_PLAIN 0
+#define MWRT_OUT_MULTICAST 1
+#define MWRT_OUT_PEERS 2
+#define MWRT_MAX_PEERS 16
+int mwrt_plan_set_output_fanout(mwrt_plan* plan, int mode, int npeer, const int64_t* peer_byte_offsets);
 /* optional band-pass: C channels x S sub-frequencies (C*S == F), host weights (C,S) or NULL = 1/S.
  * Outputs of the forward calls become (P,C,A). */
 int mwrt_plan_set_bandpass(mwrt_plan* plan, int C, int S, const double* weights);

@@ -38,12 +38,12 @@ int rte_launch(int P, int L, int F, int A, const double* tk, const double* awet,
                const double* aliq, const double* aice, const double* ds, const double* z,
                const double* amass, const double* frq, int from_sat, double emis, double* tbtotal,
                double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
-               double* tauice, double* tau_layer, int tl_angle, int* status, cudaStream_t st);
+               double* tauice, double* tau_layer, int tl_angle, int* status, const Fanout& fo, cudaStream_t st);
 int slant_path_launch(int P, int L, int A, const double* z, const double* p, const double* tk,
                       const double* e, const double* angles, int ray_tracing, double* ds, int* status,
                       cudaStream_t st);
 int bandpass_launch(int P, int C, int S, int A, const double* in, const double* w, double* out,
-                    cudaStream_t st);
+                    const Fanout& fo, cudaStream_t st);
 int dfma_peak(double* flops, double* mhz);
 int stats_launch(int T, long long M, const double* values, const double* refs, double* bias,
                  double* sd, double* rmse, double* nvalid, cudaStream_t st);
@@ -87,6 +87,7 @@ struct mwrt_plan {
   // workspace for `cap` profiles, in `nslots` (1 or 2) independent slots: with two slots kernel 3 of
   // chunk c runs on `s_aux` while kernel 1 of chunk c+1 runs on the caller's stream
   int cap, nslots, split;
+  Fanout fanout;     // how kernel 3 (or the band-pass epilogue) stores the (P,F,A) results
   struct Slot {
     double *awet, *adry, *aliq, *aice, *ds, *e;
     double* mono[7];  // monochromatic RTE outputs when band-pass is on
@@ -230,14 +231,14 @@ int mwrt_rte_f64(int P, int L, int F, int A, const double* tk, const double* awe
     return fail_arg(MWRT_E_ARG, "mwrt_rte_f64: tau_layer_angle out of range");
   return rte_launch(P, L, F, A, tk, awet, adry, aliq, aice, ds, nullptr, nullptr, frq, from_sat, emissivity, tbtotal,
                     tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tau_layer_angle, status,
-                    (cudaStream_t)stream);
+                    Fanout{MWRT_OUT_PLAIN, 0, {0}}, (cudaStream_t)stream);
 }
 
 int mwrt_bandpass_f64(int P, int C, int S, int A, const double* in, const double* w, double* out,
                       void* stream) {
   if (P <= 0 || C <= 0 || S <= 0 || A <= 0 || !in || !out)
     return fail_arg(MWRT_E_ARG, "mwrt_bandpass_f64: bad argument");
-  return bandpass_launch(P, C, S, A, in, w, out, (cudaStream_t)stream);
+  return bandpass_launch(P, C, S, A, in, w, out, Fanout{MWRT_OUT_PLAIN, 0, {0}}, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------ plan
@@ -365,6 +366,20 @@ int mwrt_plan_set_emissivity(mwrt_plan* pl, double es) {
   return 0;
 }
 
+int mwrt_plan_set_output_fanout(mwrt_plan* pl, int mode, int npeer, const int64_t* peer_byte_offsets) {
+  if (!pl || mode < MWRT_OUT_PLAIN || mode > MWRT_OUT_PEERS)
+    return fail_arg(MWRT_E_ARG, "mwrt_plan_set_output_fanout: bad argument");
+  Fanout f{mode, 0, {0}};
+  if (mode == MWRT_OUT_PEERS) {
+    if (npeer < 1 || npeer > MWRT_MAX_PEERS || !peer_byte_offsets)
+      return fail_arg(MWRT_E_ARG, "mwrt_plan_set_output_fanout: 1..MWRT_MAX_PEERS byte offsets required");
+    f.n = npeer;
+    for (int r = 0; r < npeer; ++r) f.off[r] = (long long)peer_byte_offsets[r];
+  }
+  pl->fanout = f;
+  return 0;
+}
+
 int mwrt_plan_set_split(mwrt_plan* pl, int pieces) {
   if (!pl || pieces < 1 || pieces > 64) return fail_arg(MWRT_E_ARG, "mwrt_plan_set_split: bad argument");
   pl->split = pieces;
@@ -431,12 +446,13 @@ static int forward_chunk(mwrt_plan* pl, int slot, int P, const mwrt_profiles& in
   rc = rte_launch(P, L, F, A, in.tk, w.awet, w.adry, cloudy ? w.aliq : nullptr,
                   cloudy ? w.aice : nullptr, rt ? w.ds : nullptr, in.z, pl->d_amass, pl->d_frq,
                   (pl->flags & MWRT_F_FROM_SAT) ? 1 : 0, pl->emis, mono[0], mono[1], mono[2], mono[3],
-                  mono[4], mono[5], mono[6], tl, 0, out.status, st_rte);
+                  mono[4], mono[5], mono[6], tl, 0, out.status,
+                  (pl->C > 0) ? Fanout{MWRT_OUT_PLAIN, 0, {0}} : pl->fanout, st_rte);
   if (rc) return rc;
   if (pl->C > 0)
     for (int i = 0; i < 7; ++i)
       if (dst[i]) {
-        rc = bandpass_launch(P, pl->C, pl->S, A, mono[i], pl->d_bpw, dst[i], st_rte);
+        rc = bandpass_launch(P, pl->C, pl->S, A, mono[i], pl->d_bpw, dst[i], pl->fanout, st_rte);
         if (rc) return rc;
       }
   if (two) {
@@ -551,6 +567,8 @@ static bool equally_spaced(const double* const* v, int n, int& k0, int& k1, ptrd
 int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const mwrt_outputs* out) {
   int rc = check_io(pl, P, in, out, "mwrt_plan_forward_host: bad argument");
   if (rc) return rc;
+  if (pl->fanout.mode != MWRT_OUT_PLAIN)
+    return fail_arg(MWRT_E_ARG, "mwrt_plan_forward_host: output fan-out is a device-entry feature");
   const int L = pl->L, F = pl->F, A = pl->A;
   const int Fo = pl->C > 0 ? pl->C : F;
   const bool cloudy = pl->flags & MWRT_F_CLOUDY;

@@ -37,6 +37,37 @@ struct ModelDev {
   int n_table;           // doubles in `tables`
 };
 
+// ---- result stores fused with the multi-GPU gather ------------------------------------------------
+// mode 0: plain store.  mode 1: the output pointer is an NVLink MULTICAST address (NVSwitch replicates
+// one `multimem.st` into the same offset of every rank's symmetric buffer).  mode 2: one plain store
+// per peer, at the pointer plus that peer's byte offset (peer-mapped symmetric buffers; offset 0 = own).
+// Either way kernel 3 itself delivers its results to every GPU and no separate collective runs.
+struct Fanout {
+  int mode, n;
+  long long off[MWRT_MAX_PEERS];
+};
+__device__ __forceinline__ void out_store_mc(double* p, double v) {
+  asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// 128-bit multicast store (16-byte aligned); multimem.st has no .v2.f64 form, the bits travel as four
+// .f32 lanes
+__device__ __forceinline__ void out_store2_mc(double* p, double v0, double v1) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p),
+               "f"(__int_as_float(__double2loint(v0))), "f"(__int_as_float(__double2hiint(v0))),
+               "f"(__int_as_float(__double2loint(v1))), "f"(__int_as_float(__double2hiint(v1)))
+               : "memory");
+}
+__device__ __forceinline__ void out_store(double* p, double v, const Fanout& fo) {
+  if (fo.mode == MWRT_OUT_PLAIN) {
+    *p = v;
+  } else if (fo.mode == MWRT_OUT_MULTICAST) {
+    out_store_mc(p, v);
+  } else {
+#pragma unroll 1
+    for (int r = 0; r < fo.n; ++r) *reinterpret_cast<double*>(reinterpret_cast<char*>(p) + fo.off[r]) = v;
+  }
+}
+
 // ---- reciprocal / division without the IEEE slow path --------------------------------------
 // MUFU.RCP64H seed (~20 bits) + one cubic Newton step (3 DFMA) -> ~2^-60 before rounding.
 // Valid for normal, finite x (all line-shape denominators are >= width^2 > 0).

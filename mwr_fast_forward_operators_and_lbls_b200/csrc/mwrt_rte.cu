@@ -83,14 +83,18 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
       const double emis, double* __restrict__ tbtotal, double* __restrict__ tbatm,
       double* __restrict__ tmr, double* __restrict__ tauwet, double* __restrict__ taudry,
       double* __restrict__ tauliq, double* __restrict__ tauice, double* __restrict__ tau_layer,
-      const int tl_angle, int* __restrict__ status) {
+      const int tl_angle, int* __restrict__ status, const Fanout fo) {
   __shared__ double etab[kExpTabN];        // exp_tb / log_tb tables (mwrt_common.cuh)
   __shared__ __align__(16) double ltab[128];
   exp_tab_stage(etab);
   log_tab_stage(ltab);
   __syncthreads();
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)P * F) return;
+  // threads past the end of the (profile, frequency) range redo the last valid pair and store
+  // nothing: every lane stays alive for the warp-cooperative result stores at the end
+  const long long idx_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npf = (long long)P * F;
+  const bool active = idx_raw < npf;
+  const long long idx = active ? idx_raw : npf - 1;
   const long long p = idx / F;
   const int jf = (int)(idx - p * F);
   const int a0 = blockIdx.y * NA;
@@ -132,7 +136,7 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
   double tsum = 0.0;       // NaN detector for the temperatures (NaN in absorption or geometry shows
                            // up in tauprof): checked once after the loop instead of per layer
   const bool want_tl = (tau_layer != nullptr) && (tl_angle >= a0) && (tl_angle < a0 + NA);
-  if (want_tl) tau_layer[row] = 0.0;
+  if (want_tl && active) tau_layer[row] = 0.0;
   constexpr int dir = FROM_SAT ? -1 : 1;
   const int lev0 = FROM_SAT ? L - 1 : 0;   // level sequence starts at the observer's end
   const double zref = PLANE ? zp[0] : 0.0;
@@ -222,7 +226,7 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
         ntau[a] = t0n * amass[a];
         tau[a] = 0.0;
       }
-      if (want_tl) tau_layer[row + j] = t0 * tl_amass;
+      if (want_tl && active) tau_layer[row + j] = t0 * tl_amass;
     } else {
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
@@ -248,7 +252,7 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
       batm[a] = fma(boftlay, trans[a] - tn, batm[a]);
       trans[a] = tn;
     }
-    if (want_tl && !PLANE) {
+    if (want_tl && !PLANE && active) {
       double tl = 0.0;
 #pragma unroll
       for (int a = 0; a < NA; ++a)
@@ -282,35 +286,103 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
   for (int a = 0; a < NS; ++a) anynan = anynan || isnan(tauprof[a]);
   const bool flagged = status && (status[p] & (MWRT_ST_NAN_INPUT | MWRT_ST_RANGE));  // earlier kernels
   const bool bad = neg || anynan || flagged;
-  if (status && neg) atomicOr(&status[p], MWRT_ST_NEG_ABS);
-  if (status && anynan && !neg && !flagged && jf == 0 && a0 == 0) atomicOr(&status[p], MWRT_ST_NAN_INPUT);
+  if (status && neg && active) atomicOr(&status[p], MWRT_ST_NEG_ABS);
+  if (status && anynan && !neg && !flagged && jf == 0 && a0 == 0 && active)
+    atomicOr(&status[p], MWRT_ST_NAN_INPUT);
   const double bbg = FROM_SAT ? emis * planck_mod(hvk, tkp[0], etab) : planck_mod(hvk, kTCosmic, etab);
-  const long long obase = idx * (long long)A + a0;
-#pragma unroll
-  for (int a = 0; a < NA; ++a) {
-    if (a0 + a >= A) break;
+
+  // cosmic background / T_mr (RTEquation.planck) and the inverse Planck function (bright), with the
+  // branch-free exp/log/reciprocal helpers: NA angles x 3 outputs would otherwise inline ~6000
+  // instructions of library slow paths here
+  // (evaluated inside the store helpers below, per field and angle: nothing is kept in arrays)
+  auto et_of = [&](int a) {
     const double tp = PLANE ? tauprof[0] * amass[a] : tauprof[a];
-    // cosmic background / T_mr (RTEquation.planck) and the inverse Planck function (bright), with the
-    // branch-free exp/log/reciprocal helpers: NA angles x 3 outputs would otherwise inline ~6000
-    // instructions of library slow paths here
-    const bool thin = tp < kExpMax;
-    const double et = exp_tb(fmax(-tp, -700.0), etab);
-    const double boftotl = thin ? fma(bbg, et, batm[a]) : batm[a];
-    const double boftmr = thin ? batm[a] * rcp_fast(1.0 - et) : batm[a];
-    const double o_tot = bright_nb(hvk, boftotl, ltab), o_atm0 = bright_nb(hvk, batm[a], ltab);
-    const double o_mr0 = bright_nb(hvk, boftmr, ltab);
-    double o_tot_ = o_tot, o_atm = o_atm0, o_mr = o_mr0;
-    double o_w = PLANE ? sw[0] * amass[a] : sw[a], o_d = PLANE ? sd[0] * amass[a] : sd[a];
-    double o_l = PLANE ? sl[0] * amass[a] : sl[a], o_i = PLANE ? si[0] * amass[a] : si[a];
-    if (bad) o_tot_ = o_atm = o_mr = o_w = o_d = o_l = o_i = nan("");
-    if (tbtotal) tbtotal[obase + a] = o_tot_;
-    if (tbatm) tbatm[obase + a] = o_atm;
-    if (tmr) tmr[obase + a] = o_mr;
-    if (tauwet) tauwet[obase + a] = o_w;
-    if (taudry) taudry[obase + a] = o_d;
-    if (tauliq) tauliq[obase + a] = o_l;
-    if (tauice) tauice[obase + a] = o_i;
-  }
+    return (tp < kExpMax) ? exp_tb(fmax(-tp, -700.0), etab) : -1.0;     // -1: opaque path
+  };
+  const double qn = nan("");
+  auto v_tot = [&](int a) {
+    const double et = et_of(a);
+    return bad ? qn : bright_nb(hvk, (et >= 0.0) ? fma(bbg, et, batm[a]) : batm[a], ltab);
+  };
+  auto v_atm = [&](int a) { return bad ? qn : bright_nb(hvk, batm[a], ltab); };
+  auto v_mr = [&](int a) {
+    const double et = et_of(a);
+    return bad ? qn : bright_nb(hvk, (et >= 0.0) ? batm[a] * rcp_fast(1.0 - et) : batm[a], ltab);
+  };
+
+  // Result stores.  A thread owns A consecutive doubles per field, so a warp owns 32*A consecutive
+  // doubles: when this kernel covers all angles (A == NA) and the field is 16-byte aligned, the warp
+  // transposes them through its private slice of shared memory and writes 16 bytes per lane, fully
+  // coalesced -- which is what makes the NVLink multicast form (Fanout mode 1: one `multimem.st.v2`
+  // per 16 bytes, replicated to every GPU by NVSwitch) as cheap as a local store.  Otherwise each
+  // value is stored on its own.
+  // (staging is per HALF warp, 16 threads x NA doubles at a time: 5 KB per CTA instead of 10 keeps the
+  // shared-memory carve-out of the SM at 32 KB; the kernel's strided row reads live on the L1)
+  // The staging slice is DYNAMIC shared memory, present only when the stores fan out to other GPUs:
+  // with plain stores the kernel keeps its small static footprint (and the larger L1) and stores each
+  // value directly, which the L2 merges well enough.
+  extern __shared__ __align__(16) double stage[];   // (kRteThreads / 2) * NA + 2 doubles, or none
+  const bool staged = fo.mode != MWRT_OUT_PLAIN;
+  const int lane = threadIdx.x & 31;
+  double* wst = stage + ((threadIdx.x - lane) / 2) * NA;
+  const long long widx0 = idx_raw - lane;                                  // first pair of this warp
+  const long long obase = idx * (long long)A + a0;
+  auto emit = [&](double* __restrict__ field, auto value) {
+    if (!field) return;
+    if (!staged) {
+      if (active) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a)
+          if (a0 + a < A) field[obase + a] = value(a);
+      }
+      return;
+    }
+    const bool coalesced = (A == NA) && ((reinterpret_cast<unsigned long long>(field) & 15ull) == 0);
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+      // the 16 threads of half h put their NA values into the warp's slice
+      if ((lane >> 4) == h) {
+#pragma unroll
+        for (int a = 0; a < NA; ++a) wst[(lane & 15) * NA + a] = value(a);
+      }
+      __syncwarp();
+      const long long hidx0 = widx0 + 16 * h;                              // first pair of this half
+      const long long hleft = npf - hidx0;
+      const int nval = (int)(hleft >= 16 ? 16 : (hleft > 0 ? hleft : 0)) * NA;   // valid doubles
+      if (coalesced) {
+        double* dst = field + hidx0 * NA;
+        const int npeer = (fo.mode == MWRT_OUT_PEERS) ? fo.n : 1;
+#pragma unroll 1
+        for (int r = 0; r < npeer; ++r) {
+          double* d = (fo.mode == MWRT_OUT_PEERS)
+                          ? reinterpret_cast<double*>(reinterpret_cast<char*>(dst) + fo.off[r]) : dst;
+#pragma unroll 1
+          for (int g = 2 * lane; g < nval; g += 64) {
+            const double v0 = wst[g], v1 = wst[g + 1];     // slice is padded by one pair
+            if (g + 1 < nval) {
+              if (fo.mode == MWRT_OUT_MULTICAST) out_store2_mc(d + g, v0, v1);
+              else *reinterpret_cast<double2*>(d + g) = make_double2(v0, v1);
+            } else {
+              if (fo.mode == MWRT_OUT_MULTICAST) out_store_mc(d + g, v0);
+              else d[g] = v0;
+            }
+          }
+        }
+      } else if (active && (lane >> 4) == h) {
+#pragma unroll 1
+        for (int a = 0; a < NA; ++a)
+          if (a0 + a < A) out_store(field + obase + a, wst[(lane & 15) * NA + a], fo);
+      }
+      __syncwarp();
+    }
+  };
+  emit(tbtotal, v_tot);
+  emit(tbatm, v_atm);
+  emit(tmr, v_mr);
+  emit(tauwet, [&](int a) { return bad ? qn : (PLANE ? sw[0] * amass[a] : sw[a]); });
+  emit(taudry, [&](int a) { return bad ? qn : (PLANE ? sd[0] * amass[a] : sd[a]); });
+  emit(tauliq, [&](int a) { return bad ? qn : (PLANE ? sl[0] * amass[a] : sl[a]); });
+  emit(tauice, [&](int a) { return bad ? qn : (PLANE ? si[0] * amass[a] : si[a]); });
 }
 
 template <int NA>
@@ -320,16 +392,17 @@ static int launch_rte_na(bool cloudy, int P, int L, int F, int A, const double* 
                          const double* frq, int from_sat, double emis, double* tbtotal,
                          double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
                          double* tauice, double* tau_layer, int tl_angle, int* status,
-                         cudaStream_t st) {
+                         const Fanout& fo, cudaStream_t st) {
   const long long n = (long long)P * F;
   dim3 grid((unsigned)((n + kRteThreads - 1) / kRteThreads), (unsigned)((A + NA - 1) / NA));
-#define MWRT_K_ARGS P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status
+#define MWRT_K_ARGS P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, fo
 #define MWRT_K_LAUNCH(C_, P_)                                                              \
   do {                                                                                     \
-    if (from_sat) k_rte<NA, C_, P_, true><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);     \
-    else k_rte<NA, C_, P_, false><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);             \
+    if (from_sat) k_rte<NA, C_, P_, true><<<grid, kRteThreads, dsm, st>>>(MWRT_K_ARGS);   \
+    else k_rte<NA, C_, P_, false><<<grid, kRteThreads, dsm, st>>>(MWRT_K_ARGS);           \
   } while (0)
   const bool plane = (ds == nullptr);
+  const size_t dsm = (fo.mode != MWRT_OUT_PLAIN) ? sizeof(double) * ((kRteThreads / 2) * NA + 2) : 0;
   if (cloudy && plane) MWRT_K_LAUNCH(true, true);
   else if (cloudy) MWRT_K_LAUNCH(true, false);
   else if (plane) MWRT_K_LAUNCH(false, true);
@@ -345,9 +418,10 @@ int rte_launch(int P, int L, int F, int A, const double* tk, const double* awet,
                const double* aliq, const double* aice, const double* ds, const double* z,
                const double* amass, const double* frq, int from_sat, double emis, double* tbtotal,
                double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
-               double* tauice, double* tau_layer, int tl_angle, int* status, cudaStream_t st) {
+               double* tauice, double* tau_layer, int tl_angle, int* status, const Fanout& fo,
+               cudaStream_t st) {
   const bool cloudy = (aliq != nullptr) && (aice != nullptr);
-#define MWRT_RTE_ARGS cloudy, P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, from_sat, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, st
+#define MWRT_RTE_ARGS cloudy, P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, from_sat, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, fo, st
   int na;
   if (A <= 1) na = 1;
   else if (A <= 2) na = 2;
@@ -503,7 +577,7 @@ int slant_path_launch(int P, int L, int A, const double* z, const double* p, con
 // ------------------------------------------------------------------------------------------------
 __global__ void k_bandpass(const long long n, const int C, const int S, const int A,
                            const double* __restrict__ in, const double* __restrict__ w,
-                           double* __restrict__ out) {
+                           double* __restrict__ out, const Fanout fo) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (p, c, a)
   if (idx >= n) return;
   const int a = (int)(idx % A);
@@ -513,13 +587,13 @@ __global__ void k_bandpass(const long long n, const int C, const int S, const in
   const double* src = in + ((p * C + c) * (long long)S) * A + a;
   double acc = 0.0;
   for (int s = 0; s < S; ++s) acc = fma(w ? w[c * S + s] : 1.0 / S, src[(long long)s * A], acc);
-  out[idx] = acc;
+  out_store(out + idx, acc, fo);
 }
 
 int bandpass_launch(int P, int C, int S, int A, const double* in, const double* w, double* out,
-                    cudaStream_t st) {
+                    const Fanout& fo, cudaStream_t st) {
   const long long n = (long long)P * C * A;
-  k_bandpass<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, C, S, A, in, w, out);
+  k_bandpass<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, C, S, A, in, w, out, fo);
   MWRT_CUDA_OK(cudaGetLastError());
   return 0;
 }

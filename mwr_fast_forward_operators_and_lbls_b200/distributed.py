@@ -163,6 +163,75 @@ class PipelinedForward:
         return self.gathered[slot][:, i].reshape(self.world * self.P_local, self.plan.Fo, self.plan.A)
 
 
+class FusedGatherForward:
+    """The gather fused into kernel 3: every rank's RTE kernel stores its results straight into the
+    gathered buffer of ALL ranks -- with NVLink multicast stores (`multimem.st`: one store, NVSwitch
+    replicates it into the same offset of every rank's symmetric buffer) or, where multicast is not
+    available, with one plain store per peer through peer-mapped memory.  No collective kernel runs:
+    nothing competes with the next step's kernels for SMs, and the 67 MB a rank produces leave over
+    NVLink while kernel 3 is still integrating ("RTE epilogue writes through peer
+    pointers").  A symmetric-memory barrier after the step orders the ranks.
+
+    Results of step s: `gathered[s % 2]`, laid out (world, nfield, P_local, F, A) on every rank
+    (double-buffered: step s+1 writes the other buffer).
+    """
+
+    def __init__(self, plan, P_local, fields, group=None, mode="auto"):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.plan, self.fields = plan, tuple(fields)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.P_local = int(P_local)
+        nf, F, A = len(self.fields), plan.Fo, plan.A
+        dev = torch.device("cuda", torch.cuda.current_device())
+        shape = (self.world, nf, self.P_local, F, A)
+        self.gathered = [symm_mem.empty(shape, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.hdl = [symm_mem.rendezvous(g, self.group) for g in self.gathered]
+        self.status = [torch.empty((self.P_local,), dtype=torch.int32, device=dev) for _ in range(2)]
+        mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.hdl]
+        if mode == "auto":
+            mode = "multicast" if all(mc) else "peers"
+        if mode == "multicast" and not all(mc):
+            raise RuntimeError("NVLink multicast is not available for this group")
+        self.mode = mode
+        self.field_bytes = self.P_local * F * A * 8
+        self.rank_bytes = nf * self.field_bytes
+        self.base = []          # per buffer: address kernel 3 is given for field 0 of this rank
+        self.offsets = []       # per buffer: byte offsets of the peers' copies (mode "peers")
+        for b in range(2):
+            own = self.gathered[b].data_ptr()
+            if mode == "multicast":
+                self.base.append(mc[b] + self.rank * self.rank_bytes)
+                self.offsets.append(None)
+            else:
+                ptrs = [int(q) for q in self.hdl[b].buffer_ptrs]
+                self.base.append(own + self.rank * self.rank_bytes)
+                self.offsets.append([q - own for q in ptrs])
+        self.step = 0
+
+    def run(self, z, p, t, rh, denliq=None, denice=None):
+        b = self.step % 2
+        # buffer b was last written two steps ago; every rank passed the barrier of the step in between
+        # after its consumers of buffer b were queued, so it is free to be overwritten
+        self.plan.set_output_fanout(self.mode, self.offsets[b])
+        out = {k: self.base[b] + i * self.field_bytes for i, k in enumerate(self.fields)}
+        out["status"] = self.status[b]
+        try:
+            self.plan.forward(z, p, t, rh, denliq, denice, fields=self.fields, out=out)
+        finally:
+            self.plan.set_output_fanout("plain")
+        self.hdl[b].barrier(channel=b)     # all ranks' stores have landed everywhere (stream-ordered)
+        self.step += 1
+        return b
+
+    def finish(self):
+        pass
+
+    def field(self, name, slot):
+        i = self.fields.index(name)
+        return self.gathered[slot][:, i].reshape(self.world * self.P_local, self.plan.Fo, self.plan.A)
+
+
 def simulate_sharded(plan, z, p, t, rh, denliq=None, denice=None, fields=None, group=None):
     """Every rank passes the FULL (P,L) device tensors (or identical copies); each computes its block
     and all ranks return the assembled (P,F,A) results."""

@@ -20,7 +20,11 @@ FIELDS = ("tbtotal", "tbatm", "tmr", "tauwet", "taudry", "tauliq", "tauice")
 
 
 def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+    if t is None:
+        return C.c_void_p(None)
+    if isinstance(t, int):          # raw device (or NVLink multicast) address
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
 
 
 def _stream():
@@ -93,6 +97,15 @@ class Plan:
         """Overlap kernel 3 of one part of the batch with kernel 1 of the next (mwrt_plan_set_split)."""
         _lib.check(self.lib.mwrt_plan_set_split(self._h, int(pieces)), "set_split")
 
+    def set_output_fanout(self, mode="plain", peer_byte_offsets=None):
+        """How kernel 3 stores the (P,F,A) results (mwrt_plan_set_output_fanout): "plain",
+        "multicast" (the `out` entries of `forward` are then NVLink multicast ADDRESSES, given as int)
+        or "peers" (one store per byte offset in `peer_byte_offsets`, 0 = own copy)."""
+        code = {"plain": 0, "multicast": 1, "peers": 2}[mode]
+        offs = list(peer_byte_offsets or [])
+        arr = (C.c_int64 * max(len(offs), 1))(*offs)
+        _lib.check(self.lib.mwrt_plan_set_output_fanout(self._h, code, len(offs), arr), "set_output_fanout")
+
     def launch_count(self, P):
         return int(self.lib.mwrt_plan_launch_count(self._h, int(P)))
 
@@ -109,7 +122,7 @@ class Plan:
         dev = z.device
         res = out if out is not None else {}
         for f in fields:
-            if f not in res:
+            if f not in res:      # (an int entry is a raw / multicast address, see set_output_fanout)
                 res[f] = torch.empty((P, self.Fo, self.A), dtype=torch.float64, device=dev)
         if self.tau_layers and "tau_layer" not in res:
             res["tau_layer"] = torch.empty((P, self.F, self.L), dtype=torch.float64, device=dev)
