@@ -119,6 +119,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--model", default=MODEL)
+    ap.add_argument("--gather", default="nccl", choices=["fused", "nccl"],
+                    help="N>1: 'fused' = kernel 3 stores its results straight into every rank's gathered "
+                         "buffer over NVLink (multicast / peer stores, no collective kernel); 'nccl' = "
+                         "all_gather_into_tensor overlapped with the next step")
+    ap.add_argument("--split", type=int, default=1,
+                    help="mwrt_plan_set_split: pieces of the device-entry batch (kernel 3 of piece c on a side "
+                         "stream while kernel 1 of piece c+1 runs); spreads the fused gather's stores in time")
     ap.add_argument("--gather-chunks", type=int, default=0,
                     help="N>1: 0 = gather of step s overlaps the kernels of step s+1 (default); k>0 = "
                          "within-step overlap over k pieces of the local shard")
@@ -132,7 +139,8 @@ def main():
     import torch.distributed as dist
     import mwr_fast_forward_operators_and_lbls_b200 as pkg
     from mwr_fast_forward_operators_and_lbls_b200 import _lib, roofline
-    from mwr_fast_forward_operators_and_lbls_b200.distributed import OverlappedForward, PipelinedForward
+    from mwr_fast_forward_operators_and_lbls_b200.distributed import (FusedGatherForward, OverlappedForward,
+                                                                     PipelinedForward)
     from mwr_fast_forward_operators_and_lbls_b200.forward import _ptr, _stream
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -153,6 +161,8 @@ def main():
     keys = ("z", "p", "t", "rh")
     dev = {k: torch.from_numpy(d[k]).cuda() for k in keys}
     plan = pkg.Plan(args.model, L, frq, ang)
+    if args.split > 1:
+        plan.set_split(args.split)
     fields = ("tbtotal", "tbatm", "tmr", "tauwet", "taudry", "tauliq")   # north_star's six outputs
     out = {k: torch.empty((P, F, A), dtype=torch.float64, device="cuda") for k in fields}
     out["status"] = torch.empty((P,), dtype=torch.int32, device="cuda")
@@ -162,9 +172,30 @@ def main():
     # runs on a side stream while step s+1 computes (double-buffered).  --gather-chunks > 0 selects the
     # within-step form instead (chunk c+1 computed while chunk c travels).
     ovl = None
+    gather_desc = "none"
     if N > 1:
-        ovl = (OverlappedForward(plan, P, fields, nchunk=args.gather_chunks) if args.gather_chunks > 0
-               else PipelinedForward(plan, P, fields))
+        if args.gather_chunks > 0:
+            ovl = OverlappedForward(plan, P, fields, nchunk=args.gather_chunks)
+            gather_desc = ("one all_gather_into_tensor of the six stacked outputs per chunk, %d chunks "
+                           "overlapped within the step" % args.gather_chunks)
+        else:
+            if args.gather == "fused":
+                try:
+                    ovl = FusedGatherForward(plan, P, fields)
+                    gather_desc = ("fused into kernel 3: every rank's RTE kernel stores its results into the "
+                                   "gathered buffer of all ranks over NVLink (%s), one symmetric-memory "
+                                   "barrier per step; no collective kernel" %
+                                   ("multimem.st multicast through NVSwitch" if ovl.mode == "multicast"
+                                    else "one store per peer"))
+                except Exception as exc:      # symmetric memory not available: plain NCCL
+                    if rank == 0:
+                        print("fused gather unavailable (%s); using NCCL" % exc, file=sys.stderr)
+                    ovl = None
+            if ovl is None:
+                ovl = PipelinedForward(plan, P, fields)
+                gather_desc = ("one all_gather_into_tensor of the six stacked outputs per step, overlapped "
+                               "with the next step's kernels (double-buffered); the last step's gather is "
+                               "inside the timed total")
 
     def step():
         if N > 1:
@@ -195,7 +226,7 @@ def main():
     # tail: the last step's gather must have landed before the clock stops
     tail0, tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tail0.record()
-    if isinstance(ovl, PipelinedForward):
+    if isinstance(ovl, (PipelinedForward, FusedGatherForward)):
         ovl.finish()
     tail1.record()
     barrier()
@@ -206,7 +237,7 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = N * P * F * A * args.steps / (total_ms * 1e-3)
-    if isinstance(ovl, PipelinedForward):
+    if isinstance(ovl, (PipelinedForward, FusedGatherForward)):
         checksum = float(ovl.field("tbtotal", res).sum().item())
     elif N > 1:
         checksum = float(res.field("tbtotal").sum().item())
@@ -320,11 +351,7 @@ def main():
             "config": {"workload": WORKLOAD, "model": args.model, "profiles_per_gpu": P, "levels": L,
                        "channels": F, "elevations": A, "parallelism": "profiles sharded by rank (dp%d)" % N,
                        "outputs": list(fields),
-                       "collective": ("none" if N == 1 else
-                                      "one all_gather_into_tensor of the six stacked outputs per step, "
-                                      + ("overlapped with the next step's kernels (double-buffered); the last "
-                                         "step's gather is inside the timed total" if args.gather_chunks <= 0
-                                         else "%d chunks overlapped within the step" % args.gather_chunks)),
+                       "collective": gather_desc,
                        "l2": "256 MiB flush between timed steps, outside the CUDA-event pairs",
                        "timing": "sum of per-step CUDA-event intervals, max over ranks"},
             "clocks": clocks,
