@@ -218,6 +218,15 @@ int mwrt_assemble_levels_f64(int S, int M, int K, int n_levels, double min_p, co
                              const double* crh, double* o_p, double* o_t, double* o_ppmv, double* o_h2o,
                              double* o_z, double* o_rh, int32_t* ok, void* stream);
 
+/* ---- next to the path: batched cloud detection + adiabatic water content --------
+ * /root/reference/python_src/preproc/derive_cloud_water.py: derive_cloud_features (:146-363) with
+ * calc_lwc (:68-142), for S profiles of L <= 256 levels, TOP-first (index 0 = top) like `Level_*`.
+ * p [hPa], t [K], z [m], rh [%] (over liquid): (S,L) device.  Out (S,L): liquid / ice water content in
+ * kg m^-3 and kg/kg (`Level_Liquid` / `Level_Ice` are the kg/kg ones); lwp, iwp (S,) [kg m^-2] or NULL. */
+int mwrt_cloud_features_f64(int S, int L, const double* p, const double* t, const double* z,
+                            const double* rh, double* lwc_kg_m3, double* lwc_kg_kg, double* iwc_kg_m3,
+                            double* iwc_kg_kg, double* lwp, double* iwp, void* stream);
+
 /* ---- measurement helper: dependent-free DFMA stream, returns achieved fp64 FLOP/s (2 per DFMA).
  * bench.py uses it as the denominator "of self-measured DFMA peak" (MEASURED_PEAKS.json has no fp64
  * figure).  Synchronises. */

@@ -73,6 +73,7 @@ SYMBOLS = {
     "mwrt_stats_f64": (C.c_int, [C.c_int, C.c_int64] + [C.c_void_p] * 7),
     "mwrt_thin_mean_f64": (C.c_int, [C.c_int] * 3 + [C.c_void_p] * 12),
     "mwrt_assemble_levels_f64": (C.c_int, [C.c_int] * 4 + [C.c_double] + [C.c_void_p] * 18),
+    "mwrt_cloud_features_f64": (C.c_int, [C.c_int, C.c_int] + [C.c_void_p] * 11),
     "mwrt_math_selftest_f64": (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mwrt_measure_dfma_peak": (C.c_int, [c_dp, c_dp]),
 }

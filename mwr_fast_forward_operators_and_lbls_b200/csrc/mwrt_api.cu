@@ -56,6 +56,9 @@ int assemble_launch(int S, int M, int K, int n_levels, double min_p, const doubl
                     double* o_p, double* o_t, double* o_ppmv, double* o_h2o, double* o_z, double* o_rh,
                     int* ok, cudaStream_t st);
 
+int cloud_features_launch(int S, int L, const double* p, const double* t, const double* z, const double* rh,
+                          double* lwc_m3, double* lwc_kg, double* iwc_m3, double* iwc_kg, double* lwp,
+                          double* iwp, cudaStream_t st);
 int math_selftest_launch(int op, long long n, const double* x, double* y, cudaStream_t st);
 
 struct mwrt_builtin_model {
@@ -757,6 +760,15 @@ int mwrt_assemble_levels_f64(int S, int M, int K, int n_levels, double min_p, co
     return fail_arg(MWRT_E_ARG, "mwrt_assemble_levels_f64: bad argument (n_levels >= 180 required)");
   return assemble_launch(S, M, K, n_levels, min_p, z, t, p, rh, n_inds, cz_km, cp, ct, cgkg, crh, o_p,
                          o_t, o_ppmv, o_h2o, o_z, o_rh, ok, (cudaStream_t)stream);
+}
+
+int mwrt_cloud_features_f64(int S, int L, const double* p, const double* t, const double* z,
+                            const double* rh, double* lwc_kg_m3, double* lwc_kg_kg, double* iwc_kg_m3,
+                            double* iwc_kg_kg, double* lwp, double* iwp, void* stream) {
+  if (S <= 0 || L <= 0 || !p || !t || !z || !rh || !lwc_kg_m3 || !lwc_kg_kg || !iwc_kg_m3 || !iwc_kg_kg)
+    return fail_arg(MWRT_E_ARG, "mwrt_cloud_features_f64: bad argument");
+  return cloud_features_launch(S, L, p, t, z, rh, lwc_kg_m3, lwc_kg_kg, iwc_kg_m3, iwc_kg_kg, lwp, iwp,
+                               (cudaStream_t)stream);
 }
 
 int mwrt_math_selftest_f64(int op, int64_t n, const double* x, double* y, void* stream) {

@@ -260,4 +260,175 @@ int assemble_launch(int S, int M, int K, int n_levels, double min_p, const doubl
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// N3: batched cloud detection + adiabatic water content, thread = one profile.
+// /root/reference/python_src/preproc/derive_cloud_water.py: derive_cloud_features :146-363 (relative-
+// humidity layers after Nandan et al. 2022, with the reference's own list handling) and calc_lwc
+// :68-142.  Arrays are TOP-first (index 0 = top), like the reference's.  The reference's `cloud_bools`
+// is bookkeeping no output depends on and is not kept.
+// ------------------------------------------------------------------------------------------------
+constexpr int kCloudMaxLevels = 256;
+constexpr int kCloudMaxLayers = 128;
+
+__device__ __forceinline__ int cloud_band(double z) {   // strict limits: -1 exactly on a band edge
+  if (z < 2000.0) return 0;
+  if (2000.0 < z && z < 6000.0) return 1;
+  if (6000.0 < z && z < 12000.0) return 2;
+  if (12000.0 < z) return 3;
+  return -1;
+}
+__device__ __forceinline__ int cloud_nearest(const double* z, int L, double x) {   // np.nanargmin(|z - x|)
+  int best = 0;
+  double bv = nan("");
+  for (int i = 0; i < L; ++i) {
+    const double d = fabs(z[i] - x);
+    if (!isnan(d) && (isnan(bv) || d < bv)) { bv = d; best = i; }
+  }
+  return best;
+}
+
+__global__ void k_cloud_features(const int S, const int L, const double* __restrict__ p_in,
+                                 const double* __restrict__ t_in, const double* __restrict__ z_in,
+                                 const double* __restrict__ rh_in, double* __restrict__ lwc_m3,
+                                 double* __restrict__ lwc_kg, double* __restrict__ iwc_m3,
+                                 double* __restrict__ iwc_kg, double* __restrict__ lwp,
+                                 double* __restrict__ iwp) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const double* p = p_in + (long long)s * L;
+  const double* t = t_in + (long long)s * L;
+  const double* z = z_in + (long long)s * L;
+  const long long ob = (long long)s * L;
+  const double rh_min[4] = {92, 90, 88, 75}, rh_max[4] = {95, 93, 90, 80}, rh_int[4] = {84, 82, 78, 70};
+  double rh[kCloudMaxLevels];
+  double tops[kCloudMaxLayers], bases[kCloudMaxLayers];
+  bool rmb[kCloudMaxLayers], rmt[kCloudMaxLayers];
+  int n = 0, nb = 0;   // tops, bases
+  // 1) RH with respect to ice below 0 C
+  for (int i = 0; i < L; ++i) {
+    double r = rh_in[ob + i];
+    const double tk = t[i];
+    if (tk < 273.15) {
+      const double tc = tk - 273.15;
+      const double el = 610.78 * exp(2.5e6 / 462 * (1 / 273.15 - 1 / (273.15 + tc)));
+      const double ei = 610.78 * exp(2.840e6 / 462 * (1 / 273.15 - 1 / (273.15 + tc)));
+      r = r * el / ei;
+    }
+    rh[i] = r;
+    lwc_m3[ob + i] = 0.0; lwc_kg[ob + i] = 0.0; iwc_m3[ob + i] = 0.0; iwc_kg[ob + i] = 0.0;
+  }
+  // 2-4) preliminary layers: RH above RH_min of the altitude band
+  bool in_cloud = false;
+  for (int i = 0; i < L; ++i) {
+    const int b = cloud_band(z[i]);
+    if (b < 0) continue;
+    if (rh[i] > rh_min[b]) {
+      if (!in_cloud && n < kCloudMaxLayers) tops[n++] = z[i];
+      in_cloud = true;
+    } else {
+      if (in_cloud && nb < kCloudMaxLayers) bases[nb++] = z[i];
+      in_cloud = false;
+    }
+  }
+  if (n == nb + 1 && nb < kCloudMaxLayers) bases[nb++] = z[L - 1];
+  n = n < nb ? n : nb;
+  // 5) bases below 500 m with a thickness under 400 m
+  int m = 0;
+  for (int i = 0; i < n; ++i)
+    if (!(bases[i] < 500.0 && fabs(bases[i] - tops[i]) < 400.0)) { bases[m] = bases[i]; tops[m] = tops[i]; ++m; }
+  n = m;
+  // 6) RH_max must be reached inside the layer
+  m = 0;
+  for (int i = 0; i < n; ++i) {
+    bool keep = true;
+    const int b = cloud_band(bases[i]);
+    if (b >= 0) {
+      const int it = cloud_nearest(z, L, tops[i]), ib = cloud_nearest(z, L, bases[i]);
+      bool any = false;
+      for (int k = it; k < ib; ++k) any = any || (rh_max[b] < rh[k]);
+      keep = any;
+    }
+    if (keep) { bases[m] = bases[i]; tops[m] = tops[i]; ++m; }
+  }
+  n = m;
+  // 7) connect layers: adjacent levels, a gap under 300 m, or a gap that stays above RH_inter
+  for (int i = 0; i < n; ++i) { rmb[i] = false; rmt[i] = false; }
+  double rh_inter = nan("");
+  for (int i = 0; i < n; ++i) {
+    const int b = cloud_band(bases[i]);
+    if (b >= 0) rh_inter = rh_int[b];
+    if (i != 0) {
+      const int ib = cloud_nearest(z, L, bases[i - 1]), it = cloud_nearest(z, L, tops[i]);
+      bool merge = false;
+      if (abs(ib - it) == 1) {
+        merge = rh[ib] > rh_inter;
+      } else if (fabs(bases[i - 1] - tops[i]) < 300.0) {
+        merge = true;
+      } else if (it > ib) {
+        double mn = nan("");
+        for (int k = ib; k < it; ++k)
+          if (!isnan(rh[k]) && (isnan(mn) || rh[k] < mn)) mn = rh[k];
+        merge = mn > rh_inter;
+      }
+      if (merge) { rmb[i - 1] = true; rmt[i] = true; }
+    }
+  }
+  {
+    int mb = 0, mt = 0;
+    for (int i = 0; i < n; ++i) {
+      if (!rmb[i]) bases[mb++] = bases[i];
+      if (!rmt[i]) tops[mt++] = tops[i];
+    }
+    n = mb < mt ? mb : mt;
+  }
+  // 8) thinner than 100 m
+  m = 0;
+  for (int i = 0; i < n; ++i)
+    if (!(fabs(bases[i] - tops[i]) < 100.0)) { bases[m] = bases[i]; tops[m] = tops[i]; ++m; }
+  n = m;
+  // calc_lwc (Chakraborty & Maitra 2011 / Nandan et al. 2022)
+  const double cp = 1003.5, Lh = 334944.0, R_L = 287.06, dgam = 9.76e-3 - 6.5e-3;
+  for (int i = 0; i < n; ++i) {
+    const int it = cloud_nearest(z, L, tops[i]), ib = cloud_nearest(z, L, bases[i]);
+    double* dst_m3;
+    double* dst_kg;
+    if (t[ib] > 273.15 && t[it] > 273.15) { dst_m3 = lwc_m3; dst_kg = lwc_kg; }
+    else if (t[ib] < 233.15 && t[it] < 233.15) { dst_m3 = iwc_m3; dst_kg = iwc_kg; }
+    else if (t[ib] > 233.15 && t[it] < 273.15) { dst_m3 = lwc_m3; dst_kg = lwc_kg; }
+    else continue;
+    for (int j = it; j < ib; ++j) {
+      const double rho = p[j] * 100 / R_L / t[j];
+      const double dz = z[j == 0 ? L - 1 : j - 1] - z[j];   // the reference's z_array[j-1] wraps at j = 0
+      const double ad = rho * cp / Lh * dgam * dz;
+      const double dh = z[j] - bases[i];
+      double w = ad * (1.239 - 0.145 * log(dh));
+      if (w < 0) w = 0;
+      dst_m3[ob + j] = w;
+      dst_kg[ob + j] = w / rho;
+    }
+  }
+  double sl = 0.0, si = 0.0;
+  for (int i = 0; i < L; ++i) {   // np.gradient(z): central differences, one-sided at the ends
+    double g;
+    if (L == 1) g = 0.0;
+    else if (i == 0) g = z[1] - z[0];
+    else if (i == L - 1) g = z[L - 1] - z[L - 2];
+    else g = (z[i + 1] - z[i - 1]) / 2.0;
+    sl += lwc_m3[ob + i] * g;
+    si += iwc_m3[ob + i] * g;
+  }
+  if (lwp) lwp[s] = fabs(sl);
+  if (iwp) iwp[s] = fabs(si);
+}
+
+int cloud_features_launch(int S, int L, const double* p, const double* t, const double* z, const double* rh,
+                          double* lwc_m3, double* lwc_kg, double* iwc_m3, double* iwc_kg, double* lwp,
+                          double* iwp, cudaStream_t st) {
+  if (L > kCloudMaxLevels) return fail_arg(MWRT_E_ARG, "cloud features: at most 256 levels");
+  k_cloud_features<<<(S + 31) / 32, 32, 0, st>>>(S, L, p, t, z, rh, lwc_m3, lwc_kg, iwc_m3, iwc_kg, lwp, iwp);
+  MWRT_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace mwrt

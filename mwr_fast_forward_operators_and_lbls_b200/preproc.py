@@ -138,3 +138,28 @@ def preprocess_sondes(height, temp, pres_hpa, hum, vital=None, clim=None, n_leve
     zoff = None if vital is None else np.where(np.asarray(vital, dtype=bool), 20.0, 0.0)
     return assemble_profiles(height, temp, pres_hpa, hum, inds, clim=clim, z_offset=zoff,
                              n_levels=n_levels)
+
+
+def derive_cloud_features(p_hpa, t_k, z_m, rh_pct):
+    """Batched `derive_cloud_features` of the reference (derive_cloud_water.py:146-363): (S,L) profiles,
+    TOP-first like `Level_*`, RH in % over liquid.  Returns dict of CUDA tensors: lwc_kg_m3, lwc_kg_kg
+    (`Level_Liquid`), iwc_kg_m3, iwc_kg_kg (`Level_Ice`) of shape (S,L) and lwp, iwp (S,) [kg m^-2]."""
+    _need_cuda()
+    lib = _lib.load()
+
+    def dev(x):
+        if isinstance(x, torch.Tensor):
+            return x.to("cuda", torch.float64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+    p, t, z, rh = dev(p_hpa), dev(t_k), dev(z_m), dev(rh_pct)
+    S, L = p.shape
+    out = {k: torch.empty((S, L), dtype=torch.float64, device="cuda")
+           for k in ("lwc_kg_m3", "lwc_kg_kg", "iwc_kg_m3", "iwc_kg_kg")}
+    out["lwp"] = torch.empty((S,), dtype=torch.float64, device="cuda")
+    out["iwp"] = torch.empty((S,), dtype=torch.float64, device="cuda")
+    _lib.check(lib.mwrt_cloud_features_f64(S, L, _ptr(p), _ptr(t), _ptr(z), _ptr(rh), _ptr(out["lwc_kg_m3"]),
+                                           _ptr(out["lwc_kg_kg"]), _ptr(out["iwc_kg_m3"]),
+                                           _ptr(out["iwc_kg_kg"]), _ptr(out["lwp"]), _ptr(out["iwp"]),
+                                           _stream()), "cloud_features")
+    torch.cuda.current_stream().synchronize()
+    return out

@@ -272,3 +272,68 @@ def test_preproc_feeds_the_forward_model(built_lib):
     ref = pv.simulate(lv[4][::-1][None] / 1000.0, lv[0][::-1][None], lv[1][::-1][None],
                       lv[5][::-1][None] / 100.0, pkg.HATPRO_FRQ, elev, "R24")["tbtotal"]
     assert np.max(np.abs(got[0, :, :, 0] - ref[0])) < 1e-3
+
+
+# ---- N3: batched cloud detection + adiabatic water content (derive_cloud_water.py) ------------------
+GOLD_CLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cloud_reference.npz")
+
+
+def test_cloud_oracle_equals_reference_output():
+    """oracle/cloud.py == the reference's own derive_cloud_features (outputs recorded by
+    tests/golden/make_cloud_golden.py from /root/reference's derive_cloud_water.py): bit-exact."""
+    from oracle import cloud
+    g = np.load(GOLD_CLD)
+    n_liq = n_ice = 0
+    for c in range(len(g["p"])):
+        o = cloud.derive_cloud_features(g["p"][c], g["t"][c], g["z"][c], g["rh"][c])
+        for a, k in ((o[0], "lwc_m3"), (o[1], "lwc_kg"), (o[3], "iwc_m3"), (o[4], "iwc_kg")):
+            assert np.array_equal(a, g[k][c], equal_nan=True), (c, k)
+        assert o[2] == g["lwp"][c] and o[5] == g["iwp"][c]
+        n_liq += bool((o[0] > 0).any())
+        n_ice += bool((o[3] > 0).any())
+    assert n_liq > 50 and n_ice > 50          # the goldens exercise both phases
+
+
+@pytest.mark.gpu
+def test_cloud_features_gpu_vs_reference_output(built_lib):
+    from mwr_fast_forward_operators_and_lbls_b200 import preproc as pp
+    g = np.load(GOLD_CLD)
+    out = pp.derive_cloud_features(g["p"], g["t"], g["z"], g["rh"])
+    for k, gk in (("lwc_kg_m3", "lwc_m3"), ("lwc_kg_kg", "lwc_kg"), ("iwc_kg_m3", "iwc_m3"),
+                  ("iwc_kg_kg", "iwc_kg"), ("lwp", "lwp"), ("iwp", "iwp")):
+        got, ref = out[k].cpu().numpy(), g[gk]
+        assert np.array_equal(got == 0.0, ref == 0.0), k          # same cloudy levels
+        nz = ref != 0.0
+        assert np.max(np.abs(got[nz] - ref[nz]) / np.abs(ref[nz])) < 1e-12, k
+
+
+@pytest.mark.gpu
+def test_cloud_features_feed_the_cloudy_forward_model(built_lib):
+    """N3 end to end: RH profile -> device cloud detection -> Level_Liquid -> cloudy TbCloudRTE path,
+    against the oracle chain (oracle cloud detection -> oracle forward model)."""
+    from mwr_fast_forward_operators_and_lbls_b200 import preproc as pp, driver
+    import mwr_fast_forward_operators_and_lbls_b200 as pkg
+    from oracle import cloud, pyrtlib_vec as pv
+    g = np.load(GOLD_CLD)
+    sel = [c for c in range(len(g["p"])) if (g["lwc_m3"][c] > 0).any()][:6]
+    p, t, z, rh = (g[k][sel] for k in ("p", "t", "z", "rh"))
+    out = pp.derive_cloud_features(p, t, z, rh)
+    T, L = len(sel), p.shape[1]
+
+    def lay(a):   # (T,L) top-first -> (L, time=T, Crop=1)
+        return np.ascontiguousarray(a.T.reshape(L, T, 1))
+    elev = np.array([90.0, 19.2])
+    got = driver.derive_tbs_arrays(lay(z), lay(p), lay(t), lay(np.minimum(rh, 100.0)), elevations=elev,
+                                   models=("R24",), level_liquid=lay(out["lwc_kg_kg"].cpu().numpy()),
+                                   level_ice=lay(out["iwc_kg_kg"].cpu().numpy()))["R24"]
+    lw = np.array([cloud.derive_cloud_features(p[i], t[i], z[i], rh[i])[1] for i in range(T)])
+    iw = np.array([cloud.derive_cloud_features(p[i], t[i], z[i], rh[i])[4] for i in range(T)])
+    gf = lambda a: np.ascontiguousarray(a[:, ::-1])           # ground-first
+    denl = driver.water_content_to_density(gf(lw), gf(p), gf(t))
+    deni = driver.water_content_to_density(gf(iw), gf(p), gf(t))
+    ref = pv.simulate(gf(z) / 1000.0, gf(p), gf(t), gf(np.minimum(rh, 100.0)) / 100.0, pkg.HATPRO_FRQ, elev,
+                      "R24", denliq=denl, denice=deni)["tbtotal"]
+    assert np.max(np.abs(got[:, :, :, 0] - ref)) < 1e-3
+    clear = pv.simulate(gf(z) / 1000.0, gf(p), gf(t), gf(np.minimum(rh, 100.0)) / 100.0, pkg.HATPRO_FRQ, elev,
+                        "R24")["tbtotal"]
+    assert np.max(np.abs(ref - clear)) > 0.5      # the detected clouds matter at 31.4 GHz
