@@ -245,8 +245,8 @@ constexpr int kSlowNone = 0, kSlowCorr = 1, kSlowExact = 2;
 
 __host__ __device__ inline int abs_smem_doubles(int nh, int no, int FB) {
   const int nop = (no + 1) & ~1;
-  // hrow, orow, fblk, fsq, dfm, dfp, dminh, dmino, then ints: hcls[nh], hord[nh], cnt[2]
-  return nh * kHS + nop * kOS + 2 * FB + 2 * nh * FB + nh + nop + (2 * nh + 2 + 1) / 2 + 1;
+  // hrow, orow, fblk, fsq, dfm, dfp, dminh, dmino, then ints: hcls[nh], hord[nh], cnt[2], hchk[nh], ochk[nop]
+  return nh * kHS + nop * kOS + 2 * FB + 2 * nh * FB + nh + nop + (3 * nh + nop + 2 + 1) / 2 + 1;
 }
 
 #ifndef MWRT_ABS_MINB
@@ -275,6 +275,8 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
   int* hcls = reinterpret_cast<int*>(dmino + nop);   // nh: H2O line class w.r.t. the 750 GHz cutoff
   int* hord = hcls + nh;                  // nh: processing order, all-in lines first
   int* cnt = hord + nh;                   // [0] all-in lines, [1] lines that contribute at all
+  int* hchk = cnt + 2;                    // nh: can this line need a correction in this block at all?
+  int* ochk = hchk + nh;                  // nop: same for the O2 lines
   __shared__ double etab[kExpTabN];             // exp_tb / log_tb tables (mwrt_common.cuh)
   __shared__ __align__(16) double ltab[128];
   exp_tab_stage(etab);
@@ -308,6 +310,13 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
   const int fb = (int)(item / ntiles);
   const long long tile = item - (long long)fb * ntiles;
   const int f0 = fb * FB;
+  // the level-point's inputs are requested before the block scratch is built: their DRAM latency
+  // hides under the staging below
+  const long long ipt = tile * kAbsThreads + threadIdx.x;
+  const bool in_range = ipt < npts;
+  const double p_mb = in_range ? p_in[ipt] : 1000.0;
+  const double tk_raw = in_range ? tk_in[ipt] : 300.0;
+  double e_mb = in_range ? e_in[ipt] : 0.0;
   if (fb != cur_fb) {
     cur_fb = fb;
     __syncthreads();   // everyone is done with the previous block's scratch (and with the tables' staging)
@@ -343,12 +352,21 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
       else if (w0_in && fl + lo > 751.0) cls = kWing1Out;
       else if (fl - hi > 751.0 || lo - fl > 751.0) cls = kAllOut;
       hcls[i] = cls;
+      // Corrections to the fast form are possible only for speed-dependent lines and for lines within
+      // 1e-3*fl (+ the 1 GHz shift margin of the fast path) of a block frequency: decided here once
+      // per CTA, so the per-thread tests run for those lines only (HATPRO: the 22 GHz line).
+      const bool sd_cap = (m.h2o_sd != 0) && (hrow[i * kHS + MWRT_H2O_W2] != 0.0 || hrow[i * kHS + MWRT_H2O_W2S] != 0.0);
+      hchk[i] = (sd_cap || dmin < 1e-3 * fl + 1.0) ? 1 : 0;
     }
     for (int i = threadIdx.x; i < nop; i += blockDim.x) {
       double fk = orow[i * kOS + MWRT_O2_F];
       double dmin = fabs(fblk[0] - fk);
       for (int j = 1; j < FB; ++j) dmin = fmin(dmin, fabs(fblk[j] - fk));
       dmino[i] = dmin;
+      // a line can be 'narrow and very close' only within 1e-3*fk + its largest mixing shift
+      // (|dnu0| + |dnu1| times a bound of 4 on den^2 and |th1| for atmospheric T, p) of a frequency
+      const double shmax = 4.0 * (fabs(orow[i * kOS + MWRT_O2_DNU0]) + fabs(orow[i * kOS + MWRT_O2_DNU1])) + 1e-6;
+      ochk[i] = ((i == 0 && m.o2_sd118) || dmin < 1e-3 * fk + shmax) ? 1 : 0;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -362,20 +380,16 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
     }
     __syncthreads();
   }
-  const long long ipt = tile * kAbsThreads + threadIdx.x;
-  if (ipt < npts) {
+  if (in_range) {
   const long long pidx = ipt / L;
   const int lev = (int)(ipt - pidx * L);
 
-  const double p_mb = p_in[ipt];
-  const double tk_raw = tk_in[ipt];
   // the branch-free exp needs bounded arguments: temperatures outside (50 K, 1000 K) are computed
   // with a stand-in and reported as NaN + status (the reference's realism window is 0..400 K)
   const bool t_ok = (tk_raw > 50.0) && (tk_raw < 1000.0);
   const double tk = t_ok ? tk_raw : 300.0;
-  double e_mb = e_in[ipt];
   const bool first = (fb == 0);
-  if (e_is_rh) e_mb = e_mb * goff_gratch_es(tk);
+  if (e_is_rh) e_mb = e_mb * goff_gratch_es(tk, etab, ltab);
   const bool in_nan = isnan(p_mb) || isnan(tk_raw) || isnan(e_mb);
   const bool in_bad = in_nan || !t_ok;
   if (first) {
@@ -400,6 +414,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
   const double rho = div_fast(ekpa * 10.0, kRvapAbs * t);
 
   const long long obase = (pidx * F + f0) * (long long)L + lev;  // + j*L per frequency
+  const double2* fsq2 = reinterpret_cast<const double2*>(fsq);   // fsq is 16-byte aligned (even offsets)
   double acc[FB];
   double tmp[FB];  // slow-path scratch (local memory, dynamically indexed)
 
@@ -486,15 +501,17 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
           basesum += 2.0 * ga.sp * ga.base + (2.0 * gb.sp * gb.base) * zb;
 #pragma unroll
           for (int j = 0; j < FB; ++j) {
-            const double u = fsq[j];
+            const double u = (j & 1) ? fsq2[j >> 1].y : fsq2[j >> 1].x;   // LDS.128: two frequencies per load
             const double va = u - h.c3a, vb = u - h.c3b;
             const double Da = fma(va, va, h.c4a), Db = fma(vb, vb, h.c4b);
             const double na = fma(h.n1a, va, h.n0a), nb = fma(h.n1b, vb, h.n0b);
             const double num = fma(nb, Da, na * Db);
             acc[j] = fma(num, rcp_nr1(Da * Db), acc[j]);
           }
-          ma = needs_corr(ga, ia, Ra[MWRT_H2O_FL]) ? kSlowCorr : kSlowNone;
-          mb = (has_b && needs_corr(gb, ib, Rb[MWRT_H2O_FL])) ? kSlowCorr : kSlowNone;
+          if (hchk[ia] | hchk[ib]) {   // uniform: almost every pair skips the per-thread tests
+            ma = (hchk[ia] && needs_corr(ga, ia, Ra[MWRT_H2O_FL])) ? kSlowCorr : kSlowNone;
+            mb = (has_b && hchk[ib] && needs_corr(gb, ib, Rb[MWRT_H2O_FL])) ? kSlowCorr : kSlowNone;
+          }
         } else {   // a pressure shift of 1 GHz or more: never in the atmosphere, but stay exact
           ma = kSlowExact;
           mb = has_b ? kSlowExact : kSlowNone;
@@ -682,7 +699,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
         const PairHot h{oa.c3, oa.c4, oa.n1, oa.n0, ob.c3, ob.c4, ob.n1, ob.n0};
 #pragma unroll
         for (int j = 0; j < FB; ++j) {
-          const double u = fsq[j];
+          const double u = (j & 1) ? fsq2[j >> 1].y : fsq2[j >> 1].x;   // LDS.128: two frequencies per load
           const double va = u - h.c3a, vb = u - h.c3b;
           const double Da = fma(va, va, h.c4a), Db = fma(vb, vb, h.c4b);
           const double na = fma(h.n1a, va, h.n0a), nb = fma(h.n1b, vb, h.n0b);
@@ -690,6 +707,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
           acc[j] = fma(num, rcp_nr1(Da * Db), acc[j]);
         }
         // rare: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency
+        if (!(ochk[k] | ochk[k + 1])) continue;   // uniform, decided per CTA
         const double fka = orow[k * kOS + MWRT_O2_F], fkb = orow[(k + 1) * kOS + MWRT_O2_F];
         const bool sda = m.o2_sd118 && k == 0 && (f_lo - oa.fcen < 10.0 * oa.df) &&
                          (oa.fcen - f_hi < 10.0 * oa.df);
@@ -768,7 +786,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
       if (f0 + j < F) aice[obase + (long long)j * L] = a;
     }
   }
-  }   // ipt < npts
+  }   // in_range
   }   // work items
 }
 
@@ -810,10 +828,17 @@ int absorption_launch(const ModelDev& m, int P, int L, int F, const double* p, c
 // RTEquation.vapor as a standalone stage
 __global__ void k_vapor(long long n, const double* __restrict__ tk, const double* __restrict__ rh,
                         double* __restrict__ e, double* __restrict__ rho) {
+  __shared__ double etab[kExpTabN];
+  __shared__ __align__(16) double ltab[128];
+  exp_tab_stage(etab);
+  log_tab_stage(ltab);
+  __syncthreads();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double t = tk[i];
-  double ev = rh[i] * goff_gratch_es(t);
+  const double t = tk[i];
+  const bool t_ok = (t > 50.0) && (t < 1000.0);     // same window as kernel 1; NaN otherwise
+  double ev = rh[i] * goff_gratch_es(t_ok ? t : 300.0, etab, ltab);
+  if (!t_ok) ev = nan("");
   e[i] = ev;
   if (rho) rho[i] = ev / ((kRWatVap * 1e-05) * t);
 }

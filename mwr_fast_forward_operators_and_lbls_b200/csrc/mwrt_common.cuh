@@ -510,13 +510,18 @@ __device__ __forceinline__ cplx sd_shape(double width0, double width2, double de
   return cdiv(num, cden);
 }
 
-// Goff-Gratch saturation vapour pressure over water [mb] (RTEquation.vapor)
-__device__ __forceinline__ double goff_gratch_es(double tk) {
-  double y = 373.16 / tk;
-  double es = -7.90298 * (y - 1.0) + 5.02808 * log10(y) -
-              1.3816e-07 * (exp10(11.344 * (1.0 - (1.0 / y))) - 1.0) +
-              0.0081328 * (exp10(-3.49149 * (y - 1.0)) - 1.0) + 3.0057148979490314;  // log10(1013.246)
-  return exp10(es);
+// Goff-Gratch saturation vapour pressure over water [mb] (RTEquation.vapor), with the
+// table-driven exp/log (10^x = exp(x ln 10), log10 y = ln y / ln 10) instead of libm's exp10/log10 and
+// their slow paths.  tk must be a physical temperature (callers substitute a stand-in otherwise).
+__device__ __forceinline__ double goff_gratch_es(double tk, const double* __restrict__ etab,
+                                                 const double* __restrict__ ltab) {
+  constexpr double kLn10 = 2.302585092994045684, kInvLn10 = 0.434294481903251828;
+  const double y = div_fast(373.16, tk);
+  const double es = -7.90298 * (y - 1.0) + 5.02808 * (log_tb(y, ltab) * kInvLn10) -
+                    1.3816e-07 * (exp_tb((11.344 * (1.0 - div_fast(1.0, y))) * kLn10, etab) - 1.0) +
+                    0.0081328 * (exp_tb((-3.49149 * (y - 1.0)) * kLn10, etab) - 1.0) +
+                    3.0057148979490314;  // log10(1013.246)
+  return exp_tb(es * kLn10, etab);
 }
 
 }  // namespace mwrt
