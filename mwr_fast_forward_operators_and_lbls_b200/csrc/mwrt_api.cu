@@ -580,9 +580,11 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
   // of inputs and ~1.2 ms of kernels for config 2), so the copy engine must start early and never
   // idle.  Measured on B200 (tools/host_trace.py): equal chunks of ~1000 profiles on two alternating
   // compute streams beat both fewer, larger chunks (late first copy, long drain) and a geometric
-  // ramp (tiny kernels are latency-bound: one kernel-3 thread walks all layers serially).
-  const int pieces = pl->split > 1 ? 2 * pl->split : 12;
-  int chunk = std::min(pl->chunk, std::max((P + pieces - 1) / pieces, 1024));
+  // ramp (tiny kernels are latency-bound: one kernel-3 thread walks all layers serially) or a taper.
+  // MWRT_HOST_PIECES overrides the piece count (tuning aid; 10 pieces of ~1000 is the optimum here).
+  static const int env_pieces = [] { const char* e = getenv("MWRT_HOST_PIECES"); return e ? atoi(e) : 0; }();
+  const int pieces = env_pieces > 0 ? env_pieces : (pl->split > 1 ? 2 * pl->split : 12);
+  int chunk = std::min(pl->chunk, std::max((P + pieces - 1) / pieces, env_pieces > 0 ? 256 : 1024));
   chunk = std::min(chunk, P);
   std::vector<int> sizes;
   for (int left = P; left > 0; left -= sizes.back()) sizes.push_back(std::min(chunk, left));
