@@ -416,3 +416,22 @@ def test_host_entry_field_subsets_nan_patch_and_layouts(pkg):
     for k in fields:
         assert np.array_equal(cpu(cdev[k]), chost[k], equal_nan=True), k
     assert np.nanmax(chost["tauliq"]) > 0.0
+
+
+def test_fused_gather_single_rank(pkg):
+    """The gather fused into kernel 3 (result stores fanned out through symmetric memory, staged and
+    coalesced per warp) on a one-rank group: must reproduce the plain stores bit for bit.  The real
+    multi-GPU check is tools/check_fused_gather.py under torchrun (profiles/r01j_scaling.txt)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MWRT_CHECK_P="777", MWRT_CHECK_NOTIME="1")
+    for mode in ("peers", "auto"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1",
+                            "--master-addr", "127.0.0.1", "--master-port", "29541",
+                            os.path.join(root, "tools", "check_fused_gather.py"), mode],
+                           capture_output=True, text=True, timeout=300, env=env, cwd=root)
+        if r.returncode == 77:
+            pytest.skip("symmetric memory is not available on this box: " + r.stdout[-300:])
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "identical on every rank: True" in r.stdout
