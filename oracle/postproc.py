@@ -10,18 +10,18 @@ from .pyrtlib_scalar import TbCloudRTE
 
 
 def stats_by_channel(values, references, n_chans):
-    """values, references: (time, n_chans).  Returns (std, bias, rmse) like the reference."""
-    std_array, bias_array, rmse_array = [], [], []
-    for i in range(n_chans):
-        n_valid = np.sum(~np.isnan(values[:, i]))
-        deviation = values[:, i] - references[:, i]
-        avg = np.nansum(deviation) / n_valid
-        std = np.sqrt(np.nansum((deviation - avg) ** 2) / n_valid)
-        rmse = np.sqrt(np.nansum(deviation ** 2) / n_valid)
-        std_array.append(std)
-        bias_array.append(avg)
-        rmse_array.append(rmse)
-    return np.array(std_array), np.array(bias_array), np.array(rmse_array)
+    """values, references: (time, n_chans).  Returns (std, bias, rmse) of model minus reference per
+    channel with the reference's conventions: NaN deviations are skipped in the sums, but the
+    divisor counts the non-NaN MODEL values only (multi_campaign_plots_and_ana.py:170).  Pinned against
+    outputs of the reference's own function (tests/golden/make_stats_golden.py)."""
+    v = np.asarray(values, dtype=np.float64)[:, :n_chans]
+    d = v - np.asarray(references, dtype=np.float64)[:, :n_chans]
+    with np.errstate(all="ignore"):
+        n = np.array([np.sum(~np.isnan(v[:, c])) for c in range(n_chans)])
+        bias = np.array([np.nansum(d[:, c]) for c in range(n_chans)]) / n
+        sd = np.sqrt(np.array([np.nansum((d[:, c] - bias[c]) ** 2) for c in range(n_chans)]) / n)
+        rmse = np.sqrt(np.array([np.nansum(d[:, c] ** 2) for c in range(n_chans)]) / n)
+    return sd, bias, rmse
 
 
 def check_for_nans(z_in, p_in, t_in, rh_in, frqs, ang):

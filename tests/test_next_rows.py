@@ -337,3 +337,27 @@ def test_cloud_features_feed_the_cloudy_forward_model(built_lib):
     clear = pv.simulate(gf(z) / 1000.0, gf(p), gf(t), gf(np.minimum(rh, 100.0)) / 100.0, pkg.HATPRO_FRQ, elev,
                         "R24")["tbtotal"]
     assert np.max(np.abs(ref - clear)) > 0.5      # the detected clouds matter at 31.4 GHz
+
+
+def test_stats_oracle_equals_reference_output():
+    """oracle stats_by_channel == the reference's own function (tests/golden/make_stats_golden.py),
+    NaN gaps in values and references included: bit-exact."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stats_reference.npz"))
+    for c in range(int(g["n"])):
+        v, r = g["v%d" % c], g["r%d" % c]
+        sd, bias, rmse = postproc.stats_by_channel(v, r, v.shape[1])
+        assert np.array_equal(sd, g["sd%d" % c], equal_nan=True)
+        assert np.array_equal(bias, g["bias%d" % c], equal_nan=True)
+        assert np.array_equal(rmse, g["rmse%d" % c], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_stats_gpu_vs_reference_output(built_lib):
+    from mwr_fast_forward_operators_and_lbls_b200 import stats
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stats_reference.npz"))
+    for c in range(int(g["n"])):
+        v, r = g["v%d" % c], g["r%d" % c]
+        sd, bias, rmse = stats.stats_by_channel(v, r, v.shape[1])
+        assert np.allclose(sd.cpu().numpy().ravel(), g["sd%d" % c], rtol=1e-12, atol=0, equal_nan=True)
+        assert np.allclose(bias.cpu().numpy().ravel(), g["bias%d" % c], rtol=1e-10, atol=1e-13, equal_nan=True)
+        assert np.allclose(rmse.cpu().numpy().ravel(), g["rmse%d" % c], rtol=1e-12, atol=0, equal_nan=True)
