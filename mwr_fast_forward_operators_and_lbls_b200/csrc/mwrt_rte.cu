@@ -73,7 +73,9 @@ __device__ __forceinline__ double layer_mean_pos(double x0, double x1, const dou
 #ifndef MWRT_RTE_MINB
 #define MWRT_RTE_MINB 3
 #endif
-template <int NA, bool CLOUDY, bool PLANE, bool FROM_SAT>
+// FANOUT selects the result-store form at compile time (plain stores, or the warp-staged stores that
+// fan out to other GPUs): the staged epilogue costs the plain kernel nothing, not even uniform registers.
+template <int NA, bool CLOUDY, bool PLANE, bool FROM_SAT, bool FANOUT>
 __global__ void __launch_bounds__(kRteThreads, (PLANE && !CLOUDY) ? MWRT_RTE_MINB : 1)
 k_rte(const int P, const int L, const int F, const int A, const double* __restrict__ tk,
       const double* __restrict__ awet, const double* __restrict__ adry,
@@ -322,21 +324,20 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
   // with plain stores the kernel keeps its small static footprint (and the larger L1) and stores each
   // value directly, which the L2 merges well enough.
   extern __shared__ __align__(16) double stage[];   // (kRteThreads / 2) * NA + 2 doubles, or none
-  const bool staged = fo.mode != MWRT_OUT_PLAIN;
+  constexpr bool staged = FANOUT;
   const int lane = threadIdx.x & 31;
   double* wst = stage + ((threadIdx.x - lane) / 2) * NA;
   const long long widx0 = idx_raw - lane;                                  // first pair of this warp
   const long long obase = idx * (long long)A + a0;
   auto emit = [&](double* __restrict__ field, auto value) {
     if (!field) return;
-    if (!staged) {
+    if constexpr (!FANOUT) {
       if (active) {
 #pragma unroll
         for (int a = 0; a < NA; ++a)
           if (a0 + a < A) field[obase + a] = value(a);
       }
-      return;
-    }
+    } else {
     const bool coalesced = (A == NA) && ((reinterpret_cast<unsigned long long>(field) & 15ull) == 0);
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
@@ -375,6 +376,7 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
       }
       __syncwarp();
     }
+    }   // FANOUT
   };
   emit(tbtotal, v_tot);
   emit(tbatm, v_atm);
@@ -398,8 +400,13 @@ static int launch_rte_na(bool cloudy, int P, int L, int F, int A, const double* 
 #define MWRT_K_ARGS P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, fo
 #define MWRT_K_LAUNCH(C_, P_)                                                              \
   do {                                                                                     \
-    if (from_sat) k_rte<NA, C_, P_, true><<<grid, kRteThreads, dsm, st>>>(MWRT_K_ARGS);   \
-    else k_rte<NA, C_, P_, false><<<grid, kRteThreads, dsm, st>>>(MWRT_K_ARGS);           \
+    if (fo.mode != MWRT_OUT_PLAIN) {                                                       \
+      if (from_sat) k_rte<NA, C_, P_, true, true><<<grid, kRteThreads, dsm, st>>>(MWRT_K_ARGS);    \
+      else k_rte<NA, C_, P_, false, true><<<grid, kRteThreads, dsm, st>>>(MWRT_K_ARGS);            \
+    } else {                                                                               \
+      if (from_sat) k_rte<NA, C_, P_, true, false><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);     \
+      else k_rte<NA, C_, P_, false, false><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);             \
+    }                                                                                      \
   } while (0)
   const bool plane = (ds == nullptr);
   const size_t dsm = (fo.mode != MWRT_OUT_PLAIN) ? sizeof(double) * ((kRteThreads / 2) * NA + 2) : 0;
