@@ -173,43 +173,57 @@ __device__ __noinline__ double o2_sd118_sf1(double df, double d1, double y) {
   const cplx one_m = cmake(2.0 * (1.0 - pxw.re), -2.0 * pxw.im);
   return cmul(cmake(1.0, y), one_m).re * rw2;
 }
-// Rayleigh liquid-water absorption per unit density [Np km^-1 / (g m^-3)]
-__device__ __noinline__ double liq_abs_unit(int liq_model, double f, double tk) {
-  cplx eps;
-  if (liq_model == 0) {  // Liebe-91 double Debye
+// Rayleigh liquid-water absorption per unit density [Np km^-1 / (g m^-3)], split into
+// the temperature-only part (once per level-point) and the per-frequency part.
+struct LiqPrep {
+  // Liebe-91 double Debye: eps0 - eps1, eps1 - eps2, eps2, fp, fs
+  // Rosenkranz-15 (dilec12): kap0, delta, sd, deltb, hdelta, then z1, z2 and 1/cnorm as complex numbers
+  double a, b, c, d, e;
+  cplx z1, icn;
+};
+__device__ __noinline__ LiqPrep liq_prepare(int liq_model, double tk) {
+  LiqPrep q;
+  q.z1 = cmake(0.0, 0.0);
+  q.icn = cmake(0.0, 0.0);
+  if (liq_model == 0) {
     const double theta1 = 1.0 - 300.0 / tk;
     const double eps0 = 77.66 - 103.3 * theta1;
     const double eps1 = 0.0671 * eps0;
     const double eps2 = 3.52;
     const double fp = (316.0 * theta1 + 146.4) * theta1 + 20.2;
-    const double fs = 39.8 * fp;
-    eps = cadd(cdiv(cmake(eps0 - eps1, 0.0), cmake(1.0, f / fp)),
-               cdiv(cmake(eps1 - eps2, 0.0), cmake(1.0, f / fs)));
-    eps.re += eps2;
-  } else {  // Rosenkranz (2015) `dilec12`
+    q.a = eps0 - eps1; q.b = eps1 - eps2; q.c = eps2; q.d = fp; q.e = 39.8 * fp;
+  } else {
     const double tc = tk - 273.15;
     const double theta = 300.0 / tk;
     const double lnth = log(theta);
-    const double kap0 = -43.7527 * exp(0.05 * lnth) + 299.504 * exp(1.47 * lnth) -
-                        399.364 * exp(2.11 * lnth) + 221.327 * exp(2.31 * lnth);
-    const double delta = 80.69715 * exp(-tc / 226.45);
-    const double sd = 1164.023 * exp(-651.4728 / (tc + 133.07));
-    const double deltb = 4.008724 * exp(-tc / 103.05);
-    const double hdelta = deltb / 2.0;
-    const double f1 = 10.46012 + 0.1454962 * tc + 0.063267156 * (tc * tc) +
-                      0.00093786645 * (tc * tc * tc);
-    const cplx z1 = cmake(-0.75 * f1, f1);
-    const cplx z2 = cmake(-4500.0, 2000.0);
-    const cplx cnorm = clog_(cdiv(z2, z1));
-    const cplx z = cmake(0.0, f);
-    cplx kappa = cmake(kap0, 0.0);
-    kappa = csub(kappa, cdiv(cscale(z, delta), cmake(sd, f)));
-    cplx chip = cdiv(cscale(clog_(cdiv(csub(z, z2), csub(z, z1))), hdelta), cnorm);
-    cplx chij = cdiv(cscale(clog_(cdiv(csub(z, cconj(z2)), csub(z, cconj(z1)))), hdelta),
-                     cconj(cnorm));
-    eps = cadd(kappa, cmake(chip.re + chij.re - deltb, chip.im + chij.im));
+    q.a = -43.7527 * exp(0.05 * lnth) + 299.504 * exp(1.47 * lnth) - 399.364 * exp(2.11 * lnth) +
+          221.327 * exp(2.31 * lnth);
+    q.b = 80.69715 * exp(-tc / 226.45);
+    q.c = 1164.023 * exp(-651.4728 / (tc + 133.07));
+    q.d = 4.008724 * exp(-tc / 103.05);
+    q.e = q.d / 2.0;
+    const double f1 = 10.46012 + 0.1454962 * tc + 0.063267156 * (tc * tc) + 0.00093786645 * (tc * tc * tc);
+    q.z1 = cmake(-0.75 * f1, f1);
+    const cplx cnorm = clog_(cdiv(cmake(-4500.0, 2000.0), q.z1));
+    q.icn = cnorm;   // kept as cnorm: the oracle divides by it (and by its conjugate)
   }
-  cplx re = cdiv(cmake(eps.re - 1.0, eps.im), cmake(eps.re + 2.0, eps.im));
+  return q;
+}
+__device__ __noinline__ double liq_abs_eval(int liq_model, const LiqPrep& q, double f) {
+  cplx eps;
+  if (liq_model == 0) {
+    eps = cadd(cdiv(cmake(q.a, 0.0), cmake(1.0, f / q.d)), cdiv(cmake(q.b, 0.0), cmake(1.0, f / q.e)));
+    eps.re += q.c;
+  } else {
+    const cplx z2 = cmake(-4500.0, 2000.0);
+    const cplx z = cmake(0.0, f);
+    cplx kappa = cmake(q.a, 0.0);
+    kappa = csub(kappa, cdiv(cscale(z, q.b), cmake(q.c, f)));
+    const cplx chip = cdiv(cscale(clog_(cdiv(csub(z, z2), csub(z, q.z1))), q.e), q.icn);
+    const cplx chij = cdiv(cscale(clog_(cdiv(csub(z, cconj(z2)), csub(z, cconj(q.z1)))), q.e), cconj(q.icn));
+    eps = cadd(kappa, cmake(chip.re + chij.re - q.d, chip.im + chij.im));
+  }
+  const cplx re = cdiv(cmake(eps.re - 1.0, eps.im), cmake(eps.re + 2.0, eps.im));
   return -0.06286 * re.im * f;
 }
 
@@ -766,10 +780,12 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
   if (aliq) {
     const double denl = denliq ? denliq[ipt] : 0.0;
     const bool wet = denl > 0.0 || isnan(denl);
+    LiqPrep lq;
+    if (wet) lq = liq_prepare(m.liq_model, tk);   // temperature-only terms, once per level-point
 #pragma unroll 1
     for (int j = 0; j < FB; ++j) {
       double a = 0.0;
-      if (wet) a = liq_abs_unit(m.liq_model, fblk[j], tk) * denl;
+      if (wet) a = liq_abs_eval(m.liq_model, lq, fblk[j]) * denl;
       if (in_bad) a = nan("");
       if (f0 + j < F) aliq[obase + (long long)j * L] = a;
     }

@@ -177,8 +177,12 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     y.xl = 0.0;
     y.xi = 0.0;
     if (CLOUDY) {
-      y.xl = layer_mean(lo.l, up.l, false, ng, ltab);
-      y.xi = layer_mean(lo.i, up.i, false, ng, ltab);
+      // cloud-free level pairs (the large majority) skip both means: exponential_integration gives
+      // exactly 0 for two zero endpoints
+      if (lo.l != 0.0 || up.l != 0.0 || lo.i != 0.0 || up.i != 0.0) {
+        y.xl = layer_mean(lo.l, up.l, false, ng, ltab);
+        y.xi = layer_mean(lo.i, up.i, false, ng, ltab);
+      }
       y.xtot = y.xtot + y.xi + y.xl;
     }
     y.bfar = planck_mod(hvk, fr.t, etab);
