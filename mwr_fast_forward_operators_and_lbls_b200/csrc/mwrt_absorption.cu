@@ -20,6 +20,7 @@
 // Absorption does not depend on the viewing angle: it is computed once and reused for all angles
 // (PyRTlib recomputes it per angle).
 #include "mwrt_common.cuh"
+#include <stdlib.h>
 
 namespace mwrt {
 
@@ -267,7 +268,7 @@ __host__ __device__ inline int abs_smem_doubles(int nh, int no, int FB) {
 #define MWRT_ABS_MINB 4
 #endif
 template <int FB>
-__global__ void __launch_bounds__(kAbsThreads, MWRT_ABS_MINB)
+__global__ void __launch_bounds__(kAbsThreads, FB > 16 ? 3 : MWRT_ABS_MINB)
 k_absorption(const ModelDev m, const long long npts, const int L, const int F, const int nfb,
              const double* __restrict__ p_in, const double* __restrict__ tk_in,
              const double* __restrict__ e_in, const int e_is_rh, double* __restrict__ e_out,
@@ -834,6 +835,14 @@ int absorption_launch(const ModelDev& m, int P, int L, int F, const double* p, c
                       const double* denliq, const double* denice, const double* frq, double* awet,
                       double* adry, double* aliq, double* aice, int* status, cudaStream_t st) {
 #define MWRT_ABS_ARGS m, P, L, F, p, tk, e, e_is_rh, e_out, rho_out, denliq, denice, frq, awet, adry, aliq, aice, status, st
+  // wide blocks for long frequency lists: the hoisted line parameters (40 % of a 14-wide block's FP64
+  // work) are then shared by twice as many frequencies, at 3 instead of 4 CTAs per SM
+  static const int wide = [] { const char* e = getenv("MWRT_ABS_WIDE"); return e ? atoi(e) : 1; }();
+  if (wide && F >= 112) {
+    if (F % 32 == 0) return launch_abs<32>(MWRT_ABS_ARGS);
+    if (F % 28 == 0) return launch_abs<28>(MWRT_ABS_ARGS);
+    if (F % 16 != 0 && F % 14 != 0) return launch_abs<32>(MWRT_ABS_ARGS);
+  }
   if (F % 16 == 0) return launch_abs<16>(MWRT_ABS_ARGS);
   if (F % 14 == 0) return launch_abs<14>(MWRT_ABS_ARGS);
   if (F <= 8) return launch_abs<8>(MWRT_ABS_ARGS);

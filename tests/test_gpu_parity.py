@@ -435,3 +435,15 @@ def test_fused_gather_single_rank(pkg):
             pytest.skip("symmetric memory is not available on this box: " + r.stdout[-300:])
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert "identical on every rank: True" in r.stdout
+
+
+@pytest.mark.parametrize("nf", [112, 128, 130, 140])
+def test_absorption_wide_frequency_blocks(pkg, ora, nf):
+    """Long frequency lists take the 28- / 32-wide kernels (incl. a ragged tail block at F=130)."""
+    d = pkg.synth_profiles(5, 50, seed=77)
+    e, _ = ora.pv.vapor(d["t"], d["rh"])
+    frq = np.linspace(18.0, 195.0, nf)
+    g = pkg.absorption("R22SD", d["p"], d["t"], e, frq)
+    awet, adry, _, _ = ora.pv.absorption("R22SD", d["p"], d["t"], e, frq)
+    assert rel_err(cpu(g["awet"]), awet) < REL
+    assert rel_err(cpu(g["adry"]), adry) < REL
