@@ -76,7 +76,14 @@ __device__ __forceinline__ double layer_mean_pos(double x0, double x1, const dou
 // FANOUT selects the result-store form at compile time (plain stores, or the warp-staged stores that
 // fan out to other GPUs): the staged epilogue costs the plain kernel nothing, not even uniform registers.
 template <int NA, bool CLOUDY, bool PLANE, bool FROM_SAT, bool FANOUT>
-__global__ void __launch_bounds__(kRteThreads, (PLANE && !CLOUDY) ? MWRT_RTE_MINB : 1)
+#ifndef MWRT_RTE_MINB_CLOUDY
+#define MWRT_RTE_MINB_CLOUDY 1
+#endif
+#ifndef MWRT_RTE_MINB_NA1
+#define MWRT_RTE_MINB_NA1 MWRT_RTE_MINB
+#endif
+__global__ void __launch_bounds__(kRteThreads, !PLANE ? 1 : (CLOUDY ? MWRT_RTE_MINB_CLOUDY
+                                                             : (NA <= 2 ? MWRT_RTE_MINB_NA1 : MWRT_RTE_MINB)))
 k_rte(const int P, const int L, const int F, const int A, const double* __restrict__ tk,
       const double* __restrict__ awet, const double* __restrict__ adry,
       const double* __restrict__ aliq, const double* __restrict__ aice,
