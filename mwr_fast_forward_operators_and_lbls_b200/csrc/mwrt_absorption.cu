@@ -252,9 +252,6 @@ struct PairHot {   // what the pair loop keeps live: 8 doubles
 
 // shared-memory line tables are LINE-major (one row per line, read with LDS.128 at immediate
 // offsets): the model's columns, then 1/f_line^2, padded to an even stride
-constexpr int kHS = MWRT_H2O_NCOL + 2;   // 20
-constexpr int kOS = MWRT_O2_NCOL + 2;    // 12
-constexpr int kH_IFL2 = MWRT_H2O_NCOL, kO_IFK2 = MWRT_O2_NCOL;
 static_assert(kHS % 2 == 0 && kOS % 2 == 0, "row strides must keep 16-byte alignment");
 constexpr int kSlowNone = 0, kSlowCorr = 1, kSlowExact = 2;
 
@@ -296,23 +293,8 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
   __shared__ __align__(16) double ltab[128];
   exp_tab_stage(etab);
   log_tab_stage(ltab);
-  for (int i = threadIdx.x; i < nh * kHS; i += blockDim.x) {
-    const int ln = i / kHS, c = i - ln * kHS;
-    double v = 0.0;
-    if (c < MWRT_H2O_NCOL) v = m.tables[c * nh + ln];
-    else if (c == kH_IFL2) { const double fl = m.tables[MWRT_H2O_FL * nh + ln]; v = 1.0 / (fl * fl); }
-    hrow[i] = v;
-  }
-  const double* OT = m.tables + MWRT_H2O_NCOL * nh;
-  for (int i = threadIdx.x; i < nop * kOS; i += blockDim.x) {
-    const int ln = i / kOS, c = i - ln * kOS;
-    const int src = ln < no ? ln : no - 1;
-    double v = 0.0;
-    if (c < MWRT_O2_NCOL) v = OT[c * no + src];
-    else if (c == kO_IFK2) { const double fk = OT[MWRT_O2_F * no + src]; v = 1.0 / (fk * fk); }
-    if (ln >= no && c == MWRT_O2_S300) v = 0.0;
-    orow[i] = v;
-  }
+  // line tables: a flat copy of the model's line-major rows (hrow and orow are contiguous)
+  for (int i = threadIdx.x; i < m.n_rows; i += blockDim.x) hrow[i] = m.rows[i];
   // Work items = (frequency block, tile of kAbsThreads points); CTA b owns the contiguous item range
   // [items*b/G, items*(b+1)/G) -- normally exactly one item (see launch_abs).
   const long long ntiles = (npts + kAbsThreads - 1) / kAbsThreads;

@@ -74,6 +74,7 @@ using namespace mwrt;
 struct mwrt_model {
   ModelDev dev;
   double* d_tables;
+  double* d_rows;
 };
 
 constexpr int kSlots = 4;   // workspace slots = compute streams of the host pipeline
@@ -163,6 +164,34 @@ int mwrt_model_create_custom(const mwrt_model_desc* d, mwrt_model** out) {
     delete m;
     return fail_cuda(e, "mwrt_model_create_custom");
   }
+  {   // line-major rows for kernel 1's staging (see ModelDev)
+    const int nhl = d->n_h2o, nol = d->n_o2, nop = (nol + 1) & ~1;
+    std::vector<double> rows((size_t)nhl * kHS + (size_t)nop * kOS, 0.0);
+    for (int i = 0; i < nhl; ++i) {
+      for (int c = 0; c < MWRT_H2O_NCOL; ++c) rows[(size_t)i * kHS + c] = d->h2o_lines[(size_t)c * nhl + i];
+      const double fl = d->h2o_lines[(size_t)MWRT_H2O_FL * nhl + i];
+      rows[(size_t)i * kHS + kH_IFL2] = 1.0 / (fl * fl);
+    }
+    double* orow = rows.data() + (size_t)nhl * kHS;
+    for (int i = 0; i < nop; ++i) {
+      const int src = i < nol ? i : nol - 1;
+      for (int c = 0; c < MWRT_O2_NCOL; ++c) orow[(size_t)i * kOS + c] = d->o2_lines[(size_t)c * nol + src];
+      const double fk = d->o2_lines[(size_t)MWRT_O2_F * nol + src];
+      orow[(size_t)i * kOS + kO_IFK2] = 1.0 / (fk * fk);
+      if (i >= nol) orow[(size_t)i * kOS + MWRT_O2_S300] = 0.0;   // dummy line: no strength
+    }
+    e = cudaMalloc(&m->d_rows, sizeof(double) * rows.size());
+    if (e == cudaSuccess)
+      e = cudaMemcpy(m->d_rows, rows.data(), sizeof(double) * rows.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(m->d_tables);
+      cudaFree(m->d_rows);
+      delete m;
+      return fail_cuda(e, "mwrt_model_create_custom");
+    }
+    m->dev.rows = m->d_rows;
+    m->dev.n_rows = (int)rows.size();
+  }
   ModelDev& v = m->dev;
   v.n_h2o = d->n_h2o; v.n_o2 = d->n_o2;
   v.h2o_sd = d->h2o_sd; v.o2_mixing = d->o2_mixing; v.o2_dens118 = d->o2_dens118;
@@ -191,6 +220,7 @@ int mwrt_model_create(const char* name, mwrt_model** out) {
 int mwrt_model_destroy(mwrt_model* m) {
   if (!m) return 0;
   cudaFree(m->d_tables);
+  cudaFree(m->d_rows);
   delete m;
   return 0;
 }

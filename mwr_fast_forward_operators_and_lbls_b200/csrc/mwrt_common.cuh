@@ -35,7 +35,15 @@ struct ModelDev {
   double n2_l, n2_m, n2_n;
   const double* tables;  // device
   int n_table;           // doubles in `tables`
+  // the same tables LINE-major, as kernel 1 stages them: n_h2o rows of kHS doubles (the columns, then
+  // 1/fl^2, padding) followed by the O2 rows of kOS doubles (columns, 1/f^2, padding), O2 padded to an
+  // even line count with a zero-strength copy of the last line.  Built once at model creation.
+  const double* rows;    // device
+  int n_rows;            // doubles in `rows`
 };
+constexpr int kHS = MWRT_H2O_NCOL + 2;   // 20
+constexpr int kOS = MWRT_O2_NCOL + 2;    // 12
+constexpr int kH_IFL2 = MWRT_H2O_NCOL, kO_IFK2 = MWRT_O2_NCOL;
 
 // ---- result stores fused with the multi-GPU gather ------------------------------------------------
 // mode 0: plain store.  mode 1: the output pointer is an NVLink MULTICAST address (NVSwitch replicates
