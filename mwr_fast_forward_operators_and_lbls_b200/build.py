@@ -12,7 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("MWRT_LIB_OUT") or os.path.join(HERE, "libmwrt.so")  # override: experiments only
-SOURCES = ["mwrt_api.cu", "mwrt_absorption.cu", "mwrt_rte.cu", "mwrt_post.cu", "mwrt_peak.cu"]
+SOURCES = ["mwrt_api.cu", "mwrt_absorption.cu", "mwrt_rte.cu", "mwrt_rte_fanout.cu", "mwrt_post.cu",
+           "mwrt_peak.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--fmad=true"]
 
@@ -38,17 +39,21 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
-    objs = []
+    objs = [os.path.join(CSRC, src.replace(".cu", ".o")) for src in SOURCES]
+    cmds = [[nvcc] + NVCC_FLAGS + os.environ.get("MWRT_NVCC_EXTRA", "").split()
+            + ["-c", os.path.join(CSRC, src), "-o", obj] for src, obj in zip(SOURCES, objs)]
+    # the translation units are independent: compile them side by side (kernel 3's template family
+    # alone takes ~2 minutes of ptxas)
+    procs = [subprocess.Popen(c, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for c in cmds]
     log = []
-    for src in SOURCES:
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = ([nvcc] + NVCC_FLAGS + os.environ.get("MWRT_NVCC_EXTRA", "").split()
-               + ["-c", os.path.join(CSRC, src), "-o", obj])
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        log.append("$ " + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + log[-1])
-        objs.append(obj)
+    failed = None
+    for c, pr in zip(cmds, procs):
+        out, _ = pr.communicate()
+        log.append("$ " + " ".join(c) + "\n" + out)
+        if pr.returncode != 0 and failed is None:
+            failed = log[-1]
+    if failed is not None:
+        raise RuntimeError("nvcc failed:\n" + failed)
     cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                   "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -1,435 +1,15 @@
-// mwrt_rte.cu -- kernels 2 and 3: slant path and the radiative-transfer integral.
-//
-// Kernel 2 (k_slant_path): RTEquation.refractivity + RTEquation.ray_tracing, or the plane-parallel
-//   diff(z)/sin(elev) the reference actually runs (the 6-argument constructor at
-//   /root/reference/python_src/proc/PyRTlib_processing.py:123 keeps ray_tracing=False).  SURVEY.md A.9.
-// Kernel 3 (k_rte): RTEquation.exponential_integration (layer optical depths), RTEquation.planck
-//   (downwelling recursion + cosmic background, or upwelling) and RTEquation.bright.  SURVEY.md A.8/A.10.
-//
-// Mapping: thread = (profile, frequency); it walks the layers once, in the oracle's order, and carries
-// NA viewing angles in registers -- the layer-mean absorption (2-4 log) and the Planck term (1 exp)
-// are computed once per layer and shared by all angles, and the NA exp(-tau) chains give the FP64 pipe
-// NA-way instruction-level parallelism.  One exp per (layer, angle): the transmission to the observer
-// is carried as a running product instead of PyRTlib's second exp(-tauprof).
-#include "mwrt_common.cuh"
-#include <type_traits>
+// mwrt_rte.cu -- kernel 3 with plain result stores (the template family lives in
+// mwrt_rte_kernel.cuh), kernel 2 (slant path) and the band-pass epilogue.
+#include "mwrt_rte_kernel.cuh"
 
 namespace mwrt {
 
-constexpr int kRteThreads = 128;
-
-// One layer of exponential_integration without the ds factor: x0 = lower level,
-// x1 = upper level.  Branch-free (selects) so the caller's layer loop stays one basic block:
-//   negative input -> NaN and `neg` (PyRTlib raises ValueError; the profile gets MWRT_ST_NEG_ABS)
-//   |x1-x0| < 1e-9 -> x1;  a zero endpoint -> mean (zeroflg) or 0;  else (x1-x0)/log(x1/x0).
-__device__ __forceinline__ double layer_mean(double x0, double x1, bool zeroflg, bool& neg,
-                                             const double* __restrict__ ltab) {
-  const bool negv = (x0 < 0.0) || (x1 < 0.0);
-  const bool close = fabs(x1 - x0) < 1e-09;
-  const bool zero = (x0 == 0.0) || (x1 == 0.0);
-  const bool use_log = !(negv || close || zero) && (x0 > 0.0) && (x1 > 0.0);  // false for NaN too
-  const double a = use_log ? x1 : 2.0, bq = use_log ? x0 : 1.0;              // keeps log_nb's domain
-  // reciprocal-multiply (<= 1.5 ulp each) instead of corrected divisions: 4 FP64 instructions fewer
-  const double lm = (x1 - x0) * rcp_fast(log_tb(a * rcp_fast(bq), ltab));
-  double r = zero ? (zeroflg ? (x1 + x0) * 0.5 : 0.0) : lm;
-  r = close ? x1 : r;
-  r = (negv || !(use_log || close || zero)) ? nan("") : r;
-  neg = neg || negv;
-  return r;
-}
-
-// modified Planck function 1/(exp(hvk/T) - 1); hvk/T is O(1e-2) for microwave frequencies.
-// T is a physical temperature here (kernel 1 flags anything outside 50..1000 K), hvk/T < 700.
-__device__ __forceinline__ double planck_mod(double hvk, double t, const double* __restrict__ etab) {
-  const double x = hvk * rcp_fast(t);
-  return rcp_fast(exp_tb(fmax(fmin(x, 700.0), -700.0), etab) - 1.0);
-}
-__device__ __forceinline__ double bright(double hvk, double b) {
-  if (b > 0.0 || isnan(b)) return hvk / log(1.0 + 1.0 / b);
-  return 0.0;
-}
-// bright() without library calls or branches: b <= 0 -> 0, NaN -> NaN, else hvk / log(1 + 1/b)
-__device__ __forceinline__ double bright_nb(double hvk, double b, const double* __restrict__ ltab) {
-  const bool pos = b > 0.0;
-  const double x = 1.0 + rcp_fast(pos ? b : 1.0);
-  const double t = hvk * rcp_fast(log_tb(x, ltab));
-  return pos ? t : (isnan(b) ? b : 0.0);
-}
-
-// layer_mean for two strictly positive endpoints (the common case): same operations, no selects
-// beyond the |x1-x0| < 1e-9 rule
-__device__ __forceinline__ double layer_mean_pos(double x0, double x1, const double* __restrict__ ltab) {
-  const double dx = x1 - x0;
-  const double lm = dx * rcp_fast(log_tb(x1 * rcp_fast(x0), ltab));
-  return (fabs(dx) < 1e-09) ? x1 : lm;
-}
-
-// PLANE = plane-parallel path: ds(a, layer) = dz(layer) * amass(a) is formed in registers from z and
-// a per-angle air-mass table (no ds array, no slant-path kernel); otherwise ds is read from (P,A,L).
-// FROM_SAT (upwelling, levels walked top-down) is a template parameter so the lower/upper level of a
-// layer is chosen at compile time instead of by per-layer selects.
-// measured on B200 (profiles/r01b_*): the plane-parallel variant is fastest capped at 128 registers
-// (4 CTAs/SM); the general variant spills there and runs best uncapped
-#ifndef MWRT_RTE_MINB
-#define MWRT_RTE_MINB 3
-#endif
-// FANOUT selects the result-store form at compile time (plain stores, or the warp-staged stores that
-// fan out to other GPUs): the staged epilogue costs the plain kernel nothing, not even uniform registers.
-template <int NA, bool CLOUDY, bool PLANE, bool FROM_SAT, bool FANOUT>
-#ifndef MWRT_RTE_MINB_CLOUDY
-#define MWRT_RTE_MINB_CLOUDY 3   // measured: 168 registers without spills, config 3 share -1 %
-#endif
-#ifndef MWRT_RTE_MINB_NA1
-#define MWRT_RTE_MINB_NA1 MWRT_RTE_MINB
-#endif
-__global__ void __launch_bounds__(kRteThreads, !PLANE ? 1 : (CLOUDY ? MWRT_RTE_MINB_CLOUDY
-                                                             : (NA <= 2 ? MWRT_RTE_MINB_NA1 : MWRT_RTE_MINB)))
-k_rte(const int P, const int L, const int F, const int A, const double* __restrict__ tk,
-      const double* __restrict__ awet, const double* __restrict__ adry,
-      const double* __restrict__ aliq, const double* __restrict__ aice,
-      const double* __restrict__ ds, const double* __restrict__ z,
-      const double* __restrict__ amass_tab, const double* __restrict__ frq,
-      const double emis, double* __restrict__ tbtotal, double* __restrict__ tbatm,
-      double* __restrict__ tmr, double* __restrict__ tauwet, double* __restrict__ taudry,
-      double* __restrict__ tauliq, double* __restrict__ tauice, double* __restrict__ tau_layer,
-      const int tl_angle, int* __restrict__ status, const Fanout fo) {
-  __shared__ double etab[kExpTabN];        // exp_tb / log_tb tables (mwrt_common.cuh)
-  __shared__ __align__(16) double ltab[128];
-  exp_tab_stage(etab);
-  log_tab_stage(ltab);
-  __syncthreads();
-  // threads past the end of the (profile, frequency) range redo the last valid pair and store
-  // nothing: every lane stays alive for the warp-cooperative result stores at the end
-  const long long idx_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long npf = (long long)P * F;
-  const bool active = idx_raw < npf;
-  const long long idx = active ? idx_raw : npf - 1;
-  const long long p = idx / F;
-  const int jf = (int)(idx - p * F);
-  const int a0 = blockIdx.y * NA;
-  const long long row = idx * (long long)L;  // (p*F + jf)*L
-  const double* tkp = tk + p * L;
-  const double* zp = PLANE ? z + p * L : nullptr;
-  const double* dsp = PLANE ? nullptr : ds + (p * A + a0) * (long long)L;
-  const double hvk = (frq[jf] * 1e9) * kPlanckH / kBoltzmannK;
-
-  double batm[NA], trans[NA], amass[NA];  // (amass in shared memory measured slower)
-  // species sums: per angle in the general case, one zenith-path sum (scaled at the end) if PLANE
-  constexpr int NS = PLANE ? 1 : NA;
-  double sw[NS], sd[NS], sl[NS], si[NS], tauprof[NS];
-#pragma unroll
-  for (int a = 0; a < NA; ++a) {
-    batm[a] = 0.0;
-    trans[a] = 1.0;
-    amass[a] = (PLANE && a0 + a < A) ? amass_tab[a0 + a] : 0.0;
-  }
-#pragma unroll
-  for (int a = 0; a < NS; ++a) { sw[a] = 0.0; sd[a] = 0.0; sl[a] = 0.0; si[a] = 0.0; tauprof[a] = 0.0; }
-
-  // PLANE: one clamp per layer on the zenith optical depth instead of one per angle.  exp_tb needs
-  // tau < 700; capping the zenith value at 700/max(amass) changes exp(-tau) only where it is < 1e-21
-  // relative to the terms it is added to.
-  double tcap = 700.0;
-  if (PLANE) {
-    double amax = 1.0;
-#pragma unroll
-    for (int a = 0; a < NA; ++a) amax = fmax(amax, fabs(amass[a]));
-    tcap = 700.0 / amax;
-  }
-  double tl_amass = 0.0;   // PLANE: air mass of the angle whose per-layer optical depths are wanted
-#pragma unroll
-  for (int a = 0; a < NA; ++a)
-    if (a0 + a == tl_angle) tl_amass = amass[a];
-
-  bool neg = false;
-  double tsum = 0.0;       // NaN detector for the temperatures (NaN in absorption or geometry shows
-                           // up in tauprof): checked once after the loop instead of per layer
-  const bool want_tl = (tau_layer != nullptr) && (tl_angle >= a0) && (tl_angle < a0 + NA);
-  if (want_tl && active) tau_layer[row] = 0.0;
-  constexpr int dir = FROM_SAT ? -1 : 1;
-  const int lev0 = FROM_SAT ? L - 1 : 0;   // level sequence starts at the observer's end
-  const double zref = PLANE ? zp[0] : 0.0;
-
-  // Software pipeline over the level sequence lev0, lev0+dir, ...:
-  //   A = level reached last, B = level being reached (already in registers), C = prefetched.
-  // The scalars of the NEXT layer (2-4 layer means, 1 Planck term: serial log/exp chains) are
-  // computed in the same basic block as the CURRENT layer's NA-angle stage, so they overlap.
-  struct Lvl { double w, d, l, i, t, z; };
-  struct Lay { double xw, xd, xl, xi, xtot, bfar, dz; };
-  auto load = [&](int lv) {
-    Lvl v;
-    v.w = awet[row + lv];
-    v.d = adry[row + lv];
-    v.l = CLOUDY ? aliq[row + lv] : 0.0;
-    v.i = CLOUDY ? aice[row + lv] : 0.0;
-    v.t = tkp[lv];
-    v.z = PLANE ? zp[lv] - zref : 0.0;
-    return v;
-  };
-  // GENERIC = false: wet and dry absorption strictly positive at both levels (decided by the caller)
-  auto prep = [&](auto generic, const Lvl& nr, const Lvl& fr, bool& ng) {
-    constexpr bool GENERIC = decltype(generic)::value;
-    // nr = level nearer to the observer, fr = farther; lower/upper depends on the direction
-    const Lvl& lo = FROM_SAT ? fr : nr;
-    const Lvl& up = FROM_SAT ? nr : fr;
-    Lay y;
-    if (GENERIC) {
-      y.xw = layer_mean(lo.w, up.w, true, ng, ltab);
-      y.xd = layer_mean(lo.d, up.d, true, ng, ltab);
-    } else {
-      y.xw = layer_mean_pos(lo.w, up.w, ltab);
-      y.xd = layer_mean_pos(lo.d, up.d, ltab);
-    }
-    y.xtot = y.xw + y.xd;
-    y.xl = 0.0;
-    y.xi = 0.0;
-    if (CLOUDY) {
-      // cloud-free level pairs (the large majority) skip both means: exponential_integration gives
-      // exactly 0 for two zero endpoints
-      if (lo.l != 0.0 || up.l != 0.0 || lo.i != 0.0 || up.i != 0.0) {
-        y.xl = layer_mean(lo.l, up.l, false, ng, ltab);
-        y.xi = layer_mean(lo.i, up.i, false, ng, ltab);
-      }
-      y.xtot = y.xtot + y.xi + y.xl;
-    }
-    y.bfar = planck_mod(hvk, fr.t, etab);
-    y.dz = up.z - lo.z;
-    return y;
-  };
-  auto all_pos = [](const Lvl& a, const Lvl& b) {
-    return (a.w > 0.0) && (b.w > 0.0) && (a.d > 0.0) && (b.d > 0.0);
-  };
-
-  Lvl lvA = load(lev0);
-  tsum = lvA.t;
-  double bnear = planck_mod(hvk, lvA.t, etab);
-  Lvl lvB = load(lev0 + dir);
-  Lay cur = prep(std::true_type{}, lvA, lvB, neg);
-  lvA = lvB;
-  lvB = load(L > 2 ? lev0 + 2 * dir : lev0 + dir);
-
-  // one step: the NA-angle stage of the current layer + the scalars of the next one
-  auto step_body = [&](auto generic, const int step) {
-    const int clev = lev0 + step * dir;          // level reached in this step
-    const int j = FROM_SAT ? clev + 1 : clev;    // layer index (upper level of the layer)
-    // next layer's scalars (discarded after the last step) + prefetch of the level after it
-    bool ng2 = false;
-    const Lay nxt = prep(generic, lvA, lvB, ng2);
-    const bool more = step + 1 < L;
-    neg = neg || (more && ng2);
-    tsum += lvA.t;
-    lvA = lvB;
-    lvB = load(step + 2 < L ? lev0 + (step + 2) * dir : clev);
-
-    const double xw = cur.xw, xd = cur.xd, xl = cur.xl, xi = cur.xi, xtot = cur.xtot;
-    const double bfar = cur.bfar, dz = cur.dz;
-    if (PLANE) {
-      sw[0] = fma(xw, dz, sw[0]);
-      sd[0] = fma(xd, dz, sd[0]);
-      if (CLOUDY) { sl[0] = fma(xl, dz, sl[0]); si[0] = fma(xi, dz, si[0]); }
-      tauprof[0] = fma(xtot, dz, tauprof[0]);
-    }
-    // per-angle work, written stage by stage over the NA angles (see exp_tb_vec)
-    double tau[NA], ntau[NA], ex[NA], den[NA], rden[NA];
-    if (PLANE) {
-      const double t0 = xtot * dz;                 // zenith optical depth of the layer
-      const double t0n = -fmin(t0, tcap);          // NaN is caught through tauprof after the loop
-#pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        ntau[a] = t0n * amass[a];
-        tau[a] = 0.0;
-      }
-      if (want_tl && active) tau_layer[row + j] = t0 * tl_amass;
-    } else {
-#pragma unroll
-      for (int a = 0; a < NA; ++a) {
-        const double dsa = (a0 + a < A) ? dsp[(long long)a * L + j] : 0.0;
-        sw[a] = fma(xw, dsa, sw[a]);
-        sd[a] = fma(xd, dsa, sd[a]);
-        if (CLOUDY) { sl[a] = fma(xl, dsa, sl[a]); si[a] = fma(xi, dsa, si[a]); }
-        tau[a] = xtot * dsa;
-        tauprof[a] += tau[a];
-      }
-#pragma unroll
-      for (int a = 0; a < NA; ++a) ntau[a] = fmax(-tau[a], -700.0);
-    }
-    exp_tb_vec<NA>(ntau, ex, etab);
-#pragma unroll
-    for (int a = 0; a < NA; ++a) den[a] = 1.0 + ex[a];
-    rcp_nr1_vec<NA>(den, rden);
-#pragma unroll
-    for (int a = 0; a < NA; ++a) {
-      // B(layer) * (trans_before - trans_after): the weight (1 - e^-tau) e^-tau_above of RTEquation.planck
-      const double boftlay = fma(bfar, ex[a], bnear) * rden[a];
-      const double tn = trans[a] * ex[a];
-      batm[a] = fma(boftlay, trans[a] - tn, batm[a]);
-      trans[a] = tn;
-    }
-    if (want_tl && !PLANE && active) {
-      double tl = 0.0;
-#pragma unroll
-      for (int a = 0; a < NA; ++a)
-        if (a0 + a == tl_angle) tl = tau[a];
-      tau_layer[row + j] = tl;
-    }
-    bnear = bfar;
-    cur = nxt;
-  };
-
-  // the two copies of the body differ only in how the next layer's means are formed; keeping each a
-  // single basic block lets the serial log/exp chains overlap the NA-angle stage.  Unrolling by two
-  // removes the register rotation of the pipeline (cur <- nxt, A <- B) in the plane-parallel kernel;
-  // the general kernel is larger and measured slower unrolled (instruction cache).
-  if (PLANE) {
-#pragma unroll 2
-    for (int step = 1; step < L; ++step) {
-      if (all_pos(lvA, lvB)) step_body(std::false_type{}, step);
-      else step_body(std::true_type{}, step);
-    }
-  } else {
-#pragma unroll 1
-    for (int step = 1; step < L; ++step) {
-      if (all_pos(lvA, lvB)) step_body(std::false_type{}, step);
-      else step_body(std::true_type{}, step);
-    }
-  }
-
-  bool anynan = isnan(tsum);
-#pragma unroll
-  for (int a = 0; a < NS; ++a) anynan = anynan || isnan(tauprof[a]);
-  const bool flagged = status && (status[p] & (MWRT_ST_NAN_INPUT | MWRT_ST_RANGE));  // earlier kernels
-  const bool bad = neg || anynan || flagged;
-  if (status && neg && active) atomicOr(&status[p], MWRT_ST_NEG_ABS);
-  if (status && anynan && !neg && !flagged && jf == 0 && a0 == 0 && active)
-    atomicOr(&status[p], MWRT_ST_NAN_INPUT);
-  const double bbg = FROM_SAT ? emis * planck_mod(hvk, tkp[0], etab) : planck_mod(hvk, kTCosmic, etab);
-
-  // cosmic background / T_mr (RTEquation.planck) and the inverse Planck function (bright), with the
-  // branch-free exp/log/reciprocal helpers: NA angles x 3 outputs would otherwise inline ~6000
-  // instructions of library slow paths here
-  // (evaluated inside the store helpers below, per field and angle: nothing is kept in arrays)
-  auto et_of = [&](int a) {
-    const double tp = PLANE ? tauprof[0] * amass[a] : tauprof[a];
-    return (tp < kExpMax) ? exp_tb(fmax(-tp, -700.0), etab) : -1.0;     // -1: opaque path
-  };
-  const double qn = nan("");
-  auto v_tot = [&](int a) {
-    const double et = et_of(a);
-    return bad ? qn : bright_nb(hvk, (et >= 0.0) ? fma(bbg, et, batm[a]) : batm[a], ltab);
-  };
-  auto v_atm = [&](int a) { return bad ? qn : bright_nb(hvk, batm[a], ltab); };
-  auto v_mr = [&](int a) {
-    const double et = et_of(a);
-    return bad ? qn : bright_nb(hvk, (et >= 0.0) ? batm[a] * rcp_fast(1.0 - et) : batm[a], ltab);
-  };
-
-  // Result stores.  A thread owns A consecutive doubles per field, so a warp owns 32*A consecutive
-  // doubles: when this kernel covers all angles (A == NA) and the field is 16-byte aligned, the warp
-  // transposes them through its private slice of shared memory and writes 16 bytes per lane, fully
-  // coalesced -- which is what makes the NVLink multicast form (Fanout mode 1: one `multimem.st.v2`
-  // per 16 bytes, replicated to every GPU by NVSwitch) as cheap as a local store.  Otherwise each
-  // value is stored on its own.
-  // (staging is per HALF warp, 16 threads x NA doubles at a time: 5 KB per CTA instead of 10 keeps the
-  // shared-memory carve-out of the SM at 32 KB; the kernel's strided row reads live on the L1)
-  // The staging slice is DYNAMIC shared memory, present only when the stores fan out to other GPUs:
-  // with plain stores the kernel keeps its small static footprint (and the larger L1) and stores each
-  // value directly, which the L2 merges well enough.
-  extern __shared__ __align__(16) double stage[];   // (kRteThreads / 2) * NA + 2 doubles, or none
-  constexpr bool staged = FANOUT;
-  const int lane = threadIdx.x & 31;
-  double* wst = stage + ((threadIdx.x - lane) / 2) * NA;
-  const long long widx0 = idx_raw - lane;                                  // first pair of this warp
-  const long long obase = idx * (long long)A + a0;
-  auto emit = [&](double* __restrict__ field, auto value) {
-    if (!field) return;
-    if constexpr (!FANOUT) {
-      if (active) {
-#pragma unroll
-        for (int a = 0; a < NA; ++a)
-          if (a0 + a < A) field[obase + a] = value(a);
-      }
-    } else {
-    const bool coalesced = (A == NA) && ((reinterpret_cast<unsigned long long>(field) & 15ull) == 0);
-#pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      // the 16 threads of half h put their NA values into the warp's slice
-      if ((lane >> 4) == h) {
-#pragma unroll
-        for (int a = 0; a < NA; ++a) wst[(lane & 15) * NA + a] = value(a);
-      }
-      __syncwarp();
-      const long long hidx0 = widx0 + 16 * h;                              // first pair of this half
-      const long long hleft = npf - hidx0;
-      const int nval = (int)(hleft >= 16 ? 16 : (hleft > 0 ? hleft : 0)) * NA;   // valid doubles
-      if (coalesced) {
-        double* dst = field + hidx0 * NA;
-        const int npeer = (fo.mode == MWRT_OUT_PEERS) ? fo.n : 1;
-#pragma unroll 1
-        for (int r = 0; r < npeer; ++r) {
-          double* d = (fo.mode == MWRT_OUT_PEERS)
-                          ? reinterpret_cast<double*>(reinterpret_cast<char*>(dst) + fo.off[r]) : dst;
-#pragma unroll 1
-          for (int g = 2 * lane; g < nval; g += 64) {
-            const double v0 = wst[g], v1 = wst[g + 1];     // slice is padded by one pair
-            if (g + 1 < nval) {
-              if (fo.mode == MWRT_OUT_MULTICAST) out_store2_mc(d + g, v0, v1);
-              else *reinterpret_cast<double2*>(d + g) = make_double2(v0, v1);
-            } else {
-              if (fo.mode == MWRT_OUT_MULTICAST) out_store_mc(d + g, v0);
-              else d[g] = v0;
-            }
-          }
-        }
-      } else if (active && (lane >> 4) == h) {
-#pragma unroll 1
-        for (int a = 0; a < NA; ++a)
-          if (a0 + a < A) out_store(field + obase + a, wst[(lane & 15) * NA + a], fo);
-      }
-      __syncwarp();
-    }
-    }   // FANOUT
-  };
-  emit(tbtotal, v_tot);
-  emit(tbatm, v_atm);
-  emit(tmr, v_mr);
-  emit(tauwet, [&](int a) { return bad ? qn : (PLANE ? sw[0] * amass[a] : sw[a]); });
-  emit(taudry, [&](int a) { return bad ? qn : (PLANE ? sd[0] * amass[a] : sd[a]); });
-  emit(tauliq, [&](int a) { return bad ? qn : (PLANE ? sl[0] * amass[a] : sl[a]); });
-  emit(tauice, [&](int a) { return bad ? qn : (PLANE ? si[0] * amass[a] : si[a]); });
-}
-
-template <int NA>
-static int launch_rte_na(bool cloudy, int P, int L, int F, int A, const double* tk,
-                         const double* awet, const double* adry, const double* aliq,
-                         const double* aice, const double* ds, const double* z, const double* amass,
-                         const double* frq, int from_sat, double emis, double* tbtotal,
-                         double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
-                         double* tauice, double* tau_layer, int tl_angle, int* status,
-                         const Fanout& fo, cudaStream_t st) {
-  const long long n = (long long)P * F;
-  dim3 grid((unsigned)((n + kRteThreads - 1) / kRteThreads), (unsigned)((A + NA - 1) / NA));
-#define MWRT_K_ARGS P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, fo
-#define MWRT_K_LAUNCH(C_, P_)                                                              \
-  do {                                                                                     \
-    if (fo.mode != MWRT_OUT_PLAIN) {                                                       \
-      if (from_sat) k_rte<NA, C_, P_, true, true><<<grid, kRteThreads, dsm, st>>>(MWRT_K_ARGS);    \
-      else k_rte<NA, C_, P_, false, true><<<grid, kRteThreads, dsm, st>>>(MWRT_K_ARGS);            \
-    } else {                                                                               \
-      if (from_sat) k_rte<NA, C_, P_, true, false><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);     \
-      else k_rte<NA, C_, P_, false, false><<<grid, kRteThreads, 0, st>>>(MWRT_K_ARGS);             \
-    }                                                                                      \
-  } while (0)
-  const bool plane = (ds == nullptr);
-  const size_t dsm = (fo.mode != MWRT_OUT_PLAIN) ? sizeof(double) * ((kRteThreads / 2) * NA + 2) : 0;
-  if (cloudy && plane) MWRT_K_LAUNCH(true, true);
-  else if (cloudy) MWRT_K_LAUNCH(true, false);
-  else if (plane) MWRT_K_LAUNCH(false, true);
-  else MWRT_K_LAUNCH(false, false);
-#undef MWRT_K_LAUNCH
-#undef MWRT_K_ARGS
-  MWRT_CUDA_OK(cudaGetLastError());
-  return 0;
-}
+int rte_launch_fanout(int P, int L, int F, int A, const double* tk, const double* awet, const double* adry,
+                      const double* aliq, const double* aice, const double* ds, const double* z,
+                      const double* amass, const double* frq, int from_sat, double emis, double* tbtotal,
+                      double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
+                      double* tauice, double* tau_layer, int tl_angle, int* status, const Fanout& fo,
+                      cudaStream_t st);   // mwrt_rte_fanout.cu
 
 // ds != null: general path (P,A,L).  ds == null: plane-parallel, z (P,L) + amass (A,) device arrays.
 int rte_launch(int P, int L, int F, int A, const double* tk, const double* awet, const double* adry,
@@ -438,25 +18,11 @@ int rte_launch(int P, int L, int F, int A, const double* tk, const double* awet,
                double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
                double* tauice, double* tau_layer, int tl_angle, int* status, const Fanout& fo,
                cudaStream_t st) {
-  const bool cloudy = (aliq != nullptr) && (aice != nullptr);
-#define MWRT_RTE_ARGS cloudy, P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, from_sat, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, fo, st
-  int na;
-  if (A <= 1) na = 1;
-  else if (A <= 2) na = 2;
-  else if (A <= 4) na = 4;
-  else if (A <= 5) na = 5;
-  else if (A <= 8) na = 8;
-  else if (A <= 10) na = 10;
-  else na = (((A + 9) / 10) * 10 <= ((A + 7) / 8) * 8) ? 10 : 8;
-  switch (na) {
-    case 1: return launch_rte_na<1>(MWRT_RTE_ARGS);
-    case 2: return launch_rte_na<2>(MWRT_RTE_ARGS);
-    case 4: return launch_rte_na<4>(MWRT_RTE_ARGS);
-    case 5: return launch_rte_na<5>(MWRT_RTE_ARGS);
-    case 8: return launch_rte_na<8>(MWRT_RTE_ARGS);
-    default: return launch_rte_na<10>(MWRT_RTE_ARGS);
-  }
-#undef MWRT_RTE_ARGS
+  if (fo.mode != MWRT_OUT_PLAIN)
+    return rte_launch_fanout(P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, from_sat, emis, tbtotal,
+                             tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, fo, st);
+  return rte_launch_t<false>(P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, from_sat, emis, tbtotal,
+                             tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, fo, st);
 }
 
 // ------------------------------------------------------------------------------------------------
