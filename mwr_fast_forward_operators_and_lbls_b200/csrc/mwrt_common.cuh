@@ -169,63 +169,15 @@ __device__ __forceinline__ double log_nb(double x) {
   return fma(ed, 6.93147180369123816490e-01, s2 + tail);
 }
 
-// The same exp over N independent arguments, written stage by stage so that the N dependency chains
-// are interleaved in program order (the FP64 pipe needs ~4 independent DFMAs in flight per scheduler;
-// left to itself the compiler serialises the chains to save registers).
-// Ordered FP64 ops: `asm volatile` keeps the compiler front end from re-serialising the N chains
-// (it otherwise schedules depth-first to save registers; measured: 52% of FP64 instructions issued
-// back-to-back dependent).  ptxas still owns the final schedule but starts from this order.
+// ---- ordered FP64 ops for the staged helpers (exp_tb_vec, rcp_nr1_vec) ---------------------------------
+// Those evaluate N independent arguments stage by stage, so that the N dependency chains are interleaved
+// in program order (the FP64 pipe needs ~4 independent DFMAs in flight per scheduler).  `asm volatile`
+// keeps the compiler front end from re-serialising the chains (left alone it schedules depth-first to
+// save registers; measured: 52 % of FP64 instructions issued back-to-back dependent).  ptxas still owns
+// the final schedule but starts from this order.
 #define MWRT_FMA(d, a, b, c) asm volatile("fma.rn.f64 %0, %1, %2, %3;" : "=d"(d) : "d"(a), "d"(b), "d"(c))
 #define MWRT_MUL(d, a, b) asm volatile("mul.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b))
 #define MWRT_ADD(d, a, b) asm volatile("add.rn.f64 %0, %1, %2;" : "=d"(d) : "d"(a), "d"(b))
-
-template <int N>
-__device__ __forceinline__ void exp_nb_vec(const double (&x)[N], double (&y)[N]) {
-  const double kMagic = 6755399441055744.0;
-  double t[N], r[N], p[N];
-  int k[N];
-#pragma unroll
-  for (int a = 0; a < N; ++a) MWRT_FMA(t[a], x[a], 1.4426950408889634, kMagic);
-#pragma unroll
-  for (int a = 0; a < N; ++a) {
-    k[a] = __double2loint(t[a]);
-    MWRT_ADD(t[a], t[a], -kMagic);
-  }
-#pragma unroll
-  for (int a = 0; a < N; ++a) MWRT_FMA(r[a], t[a], -6.93147180369123816490e-01, x[a]);
-#pragma unroll
-  for (int a = 0; a < N; ++a) MWRT_FMA(r[a], t[a], -1.90821492927058770002e-10, r[a]);
-#pragma unroll
-  for (int a = 0; a < N; ++a) MWRT_FMA(p[a], r[a], 1.6059043836821613e-10, 2.08767569878681e-09);
-  const double c[11] = {2.505210838544172e-08, 2.755731922398589e-07, 2.7557319223985893e-06,
-                        2.48015873015873e-05,  1.984126984126984e-04, 1.388888888888889e-03,
-                        8.333333333333333e-03, 4.1666666666666664e-02, 1.6666666666666666e-01,
-                        0.5,                   1.0};
-#pragma unroll
-  for (int i = 0; i < 11; ++i) {
-#pragma unroll
-    for (int a = 0; a < N; ++a) MWRT_FMA(p[a], p[a], r[a], c[i]);
-  }
-#pragma unroll
-  for (int a = 0; a < N; ++a) MWRT_FMA(p[a], p[a], r[a], 1.0);
-#pragma unroll
-  for (int a = 0; a < N; ++a)
-    y[a] = __hiloint2double(__double2hiint(p[a]) + (k[a] << 20), __double2loint(p[a]));
-}
-
-// N reciprocals, staged like exp_nb_vec
-template <int N>
-__device__ __forceinline__ void rcp_fast_vec(const double (&x)[N], double (&y)[N]) {
-  double r[N], e[N];
-#pragma unroll
-  for (int a = 0; a < N; ++a) asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[a]) : "d"(x[a]));
-#pragma unroll
-  for (int a = 0; a < N; ++a) MWRT_FMA(e[a], -x[a], r[a], 1.0);
-#pragma unroll
-  for (int a = 0; a < N; ++a) MWRT_FMA(e[a], e[a], e[a], e[a]);
-#pragma unroll
-  for (int a = 0; a < N; ++a) MWRT_FMA(y[a], r[a], e[a], r[a]);
-}
 
 // ---- table-driven exp: 8 FP64-pipe instructions -------------------------------------------------
 // exp(x) = 2^k * T[j] * exp(r),  n = round(x*256/ln2) = 256 k + j,  r = x - n*ln2/256, |r| <= ln2/512:
@@ -322,7 +274,7 @@ __device__ __forceinline__ double exp_tb(double x, const double* __restrict__ ta
   return __hiloint2double(__double2hiint(p) + ((n >> 8) << 20), __double2loint(p));
 }
 
-// N independent arguments, stage by stage (see exp_nb_vec)
+// N independent arguments, stage by stage (see the note on ordered FP64 ops above)
 template <int N>
 __device__ __forceinline__ void exp_tb_vec(const double (&x)[N], double (&y)[N],
                                            const double* __restrict__ tab) {
@@ -461,62 +413,7 @@ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
     return cplx{(a.re * r + a.im) * d, (a.im * r - a.re) * d};
   }
 }
-__device__ __forceinline__ cplx csqrt_(cplx z) {
-  double m = hypot(z.re, z.im);
-  if (m == 0.0) return cplx{0.0, 0.0};
-  double t = sqrt(0.5 * (m + fabs(z.re)));
-  if (z.re >= 0.0) return cplx{t, z.im / (2.0 * t)};
-  return cplx{fabs(z.im) / (2.0 * t), copysign(t, z.im)};
-}
-__device__ __forceinline__ cplx cexp_(cplx z) {
-  double e = exp(z.re), s, c;
-  sincos(z.im, &s, &c);
-  return cplx{e * c, e * s};
-}
 __device__ __forceinline__ cplx clog_(cplx z) { return cplx{log(hypot(z.re, z.im)), atan2(z.im, z.re)}; }
-
-// Complex error function w(x+iy): Hui, Armstrong & Wray 6th-order rational approximation
-// (Rosenkranz `dcerror`, as in pyrtlib.utils.dcerror).
-__device__ __forceinline__ cplx dcerror(double x, double y) {
-  const double a0 = 122.607931777104326, a1 = 214.382388694706425, a2 = 181.928533092181549,
-               a3 = 93.155580458138441, a4 = 30.180142196210589, a5 = 5.912626209773153,
-               a6 = 0.564189583562615;
-  const double b0 = 122.607931773875350, b1 = 352.730625110963558, b2 = 457.334478783897737,
-               b3 = 348.703917719495792, b4 = 170.354001821091472, b5 = 53.992906912940207,
-               b6 = 10.479857114260399;
-  cplx zh = cmake(fabs(y), -x);
-  cplx as = cmake(a6 * zh.re + a5, a6 * zh.im);
-  as = cmul(as, zh); as.re += a4;
-  as = cmul(as, zh); as.re += a3;
-  as = cmul(as, zh); as.re += a2;
-  as = cmul(as, zh); as.re += a1;
-  as = cmul(as, zh); as.re += a0;
-  cplx bs = cmake(zh.re + b6, zh.im);
-  bs = cmul(bs, zh); bs.re += b5;
-  bs = cmul(bs, zh); bs.re += b4;
-  bs = cmul(bs, zh); bs.re += b3;
-  bs = cmul(bs, zh); bs.re += b2;
-  bs = cmul(bs, zh); bs.re += b1;
-  bs = cmul(bs, zh); bs.re += b0;
-  cplx w = cdiv(as, bs);
-  if (y >= 0.0) return w;
-  cplx z = cmake(x, y);
-  cplx z2 = cmul(z, z);
-  cplx ex = cexp_(cmake(-z2.re, -z2.im));
-  return cmake(2.0 * ex.re - w.re, 2.0 * ex.im + w.im);
-}
-
-// Real part of the speed-dependent resonant shape factor (H2O 22/183 GHz):
-//   xc = (w0 - 1.5 w2 + i (df + 1.5 d2)) / (w2 - i d2);  sd = 2 (1 - sqrt(pi) xrt w(i xrt)) / (w2 - i d2)
-__device__ __forceinline__ cplx sd_shape(double width0, double width2, double delta2, double df) {
-  cplx cden = cmake(width2, -delta2);
-  cplx xc = cdiv(cmake(width0 - 1.5 * width2, df + 1.5 * delta2), cden);
-  cplx xrt = csqrt_(xc);
-  cplx w = dcerror(-xrt.im, xrt.re);
-  cplx pxw = cscale(cmul(xrt, w), kSqrtPi);
-  cplx num = cmake(2.0 * (1.0 - pxw.re), -2.0 * pxw.im);
-  return cdiv(num, cden);
-}
 
 // Goff-Gratch saturation vapour pressure over water [mb] (RTEquation.vapor), with the
 // table-driven exp/log (10^x = exp(x ln 10), log10 y = ln y / ln 10) instead of libm's exp10/log10 and
