@@ -144,15 +144,18 @@ int mwrt_bandpass_f64(int P, int C, int S, int A, const double* in, const double
 /* ---- the fused path: replaces TbCloudRTE(...).execute() for a batch of profiles ----------------
  * A plan fixes (model, L, F, A, frq, angles, flags) and owns device copies of frq/angles, the
  * intermediate (P_chunk,F,L) absorption workspace, and -- for the host entry point -- streams, events
- * and staging buffers.  frq/angles are HOST pointers here.  chunk_profiles <= 0 picks a default. */
+ * and staging buffers.  frq/angles are HOST pointers here.  chunk_profiles <= 0 picks a default.
+ * Threading: mwrt_model handles are immutable and may be shared; a plan owns its workspace, so ONE
+ * forward call at a time per plan (use one plan per host thread / stream). */
 int mwrt_plan_create(const mwrt_model* m, int L, int F, int A, const double* frq, const double* angles,
                      int flags, int chunk_profiles, mwrt_plan** out);
 int mwrt_plan_destroy(mwrt_plan* plan);
 int mwrt_plan_set_emissivity(mwrt_plan* plan, double es);
 /* pieces > 1: mwrt_plan_forward_device cuts the batch into `pieces` parts and overlaps kernel 3 of
  * part c (on a stream owned by the plan) with kernel 1 of part c+1 (on the caller's stream); the
- * caller's stream still completes after everything.  The host entry point uses 2*pieces chunks.
- * Default 1 (no split). */
+ * caller's stream still completes after everything.  The host entry point runs equal chunks of ~1000
+ * profiles (2*pieces chunks once pieces > 1) on two alternating compute streams; MWRT_TRACE=1 in the
+ * environment prints its per-chunk timeline.  Default 1 (no split). */
 int mwrt_plan_set_split(mwrt_plan* plan, int pieces);
 /* Multi-GPU gather fused into the result stores ("RTE epilogue writes through peer
  * pointers").  The (P,F,A) result pointers handed to mwrt_plan_forward_device are then written
