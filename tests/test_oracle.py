@@ -148,3 +148,25 @@ def test_nan_profile_gives_nan_and_batch_continues():
 def test_negative_absorption_raises_like_upstream():
     with pytest.raises(ValueError):
         ps.exponential_integration(True, np.array([1.0, -1.0, 2.0]), np.array([0.0, 1.0, 1.0]), 0, 3, 1)
+
+
+def test_specific_attenuation_matches_textbook_values():
+    """External sanity anchor for the from-memory line tables (NOT parity): at sea level (1013.25 hPa,
+    15 C, 7.5 g m^-3 of vapour) the restatement gives the specific attenuations every microwave
+    propagation text quotes for that state (ITU-R P.676-class curves): ~0.18 dB/km at the 22.235 GHz
+    water line, ~29 dB/km at 183.31 GHz, ~15 dB/km in the 60 GHz oxygen complex, ~1.3 dB/km at the
+    118.75 GHz oxygen line, ~0.4 dB/km of vapour at 94 GHz.  12 % windows: the point is to catch a
+    mis-remembered strength, width or unit, not to validate digits."""
+    from oracle import pyrtlib_vec as pv
+    p, t = np.array([[1013.25]]), np.array([[288.15]])
+    e = np.array([[7.5e-3 * 461.5 * 288.15 / 100.0]])          # 7.5 g m^-3 -> mb
+    frq = np.array([22.235, 183.31, 60.0, 118.75, 94.0])
+    db = 10.0 / np.log(10.0)
+    expect_wet = {0: 0.18, 1: 29.0, 4: 0.38}
+    expect_dry = {2: 14.8, 3: 1.33}
+    for mdl in ("R98", "R17", "R20", "R24", "R22SD"):
+        awet, adry, _, _ = pv.absorption(mdl, p, t, e, frq)
+        for j, v in expect_wet.items():
+            assert abs(awet[0, j, 0] * db - v) < 0.12 * v, (mdl, frq[j], awet[0, j, 0] * db)
+        for j, v in expect_dry.items():
+            assert abs(adry[0, j, 0] * db - v) < 0.12 * v, (mdl, frq[j], adry[0, j, 0] * db)
