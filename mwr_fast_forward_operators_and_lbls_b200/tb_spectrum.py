@@ -14,6 +14,8 @@ Same names, argument meaning and error behaviour as upstream:
 unknown model -> ValueError; negative absorption in the layer integration -> ValueError;
 inputs are never modified.  Unlike upstream, all angles share one absorption computation.
 """
+import threading
+
 import numpy as np
 import pandas as pd
 import torch
@@ -76,22 +78,25 @@ class TbCloudRTE:
     def execute(self, only_bt=True):
         if self._model is None:
             raise ValueError("init_absmdl() must be called before execute()")
-        plan = Plan(self._model, self.nl, self.frq, self.angles, ray_tracing=self.ray_tracing,
-                    from_sat=self.satellite, cloudy=self.cloudy, tau_layers=False,
-                    emissivity=self.emissivity)
         dl = di = None
         if self.cloudy:
             dl, di = _dev64(self.denliq[None]), _dev64(self.denice[None])
-        res = plan.forward(_dev64(self.z[None]), _dev64(self.p[None]), _dev64(self.tk[None]),
-                           _dev64(self.rh[None]), dl, di)
-        torch.cuda.current_stream().synchronize()
-        status = int(res["status"][0].item())
+        # one device buffer for all fields -> one device-to-host copy
+        buf = torch.empty((len(FIELDS), 1, self.nf, self.nang), dtype=torch.float64, device="cuda")
+        out = {f: buf[i] for i, f in enumerate(FIELDS)}
+        with _PLAN_LOCK:                  # cached plans are shared; a plan runs one call at a time
+            plan = _cached_plan(self._model, self.nl, self.frq, self.angles, self.ray_tracing,
+                                self.satellite, self.cloudy, self.emissivity)
+            res = plan.forward(_dev64(self.z[None]), _dev64(self.p[None]), _dev64(self.tk[None]),
+                               _dev64(self.rh[None]), dl, di, out=out)
+            host = buf.cpu().numpy()      # synchronises the stream
+            status = int(res["status"][0].item())
         if status & _lib.ST_NEG_ABS:
             raise ValueError("Error encountered in exponential_integration")  # upstream's message
         cols = {}
         for c in COLUMNS:
             if c in FIELDS:
-                cols[c] = res[c][0].cpu().numpy().T.reshape(self.nf * self.nang)  # angle-major
+                cols[c] = host[FIELDS.index(c), 0].T.reshape(self.nf * self.nang)  # angle-major
             else:
                 cols[c] = np.zeros(self.nf * self.nang)
         df = pd.DataFrame(cols)
@@ -99,3 +104,26 @@ class TbCloudRTE:
         df["frq"] = np.tile(self.frq, self.nang)
         self.status = status
         return df
+
+
+# The reference builds a fresh TbCloudRTE for every (profile, elevation, model)
+# (PyRTlib_processing.py:99-151: 41 680 objects per run, but only 10 elevations x 4 models x 1 level
+# count of distinct configurations).  Plans -- device copies of frq/angles, workspace, streams -- are
+# therefore cached per configuration; a plan is used by one execute() at a time.
+_PLAN_CACHE = {}
+_PLAN_CACHE_MAX = 64
+_PLAN_LOCK = threading.Lock()
+
+
+def _cached_plan(model, nl, frq, angles, ray_tracing, from_sat, cloudy, emissivity):
+    key = (model.name if hasattr(model, "name") else id(model), id(model), int(nl), frq.tobytes(),
+           angles.tobytes(), bool(ray_tracing), bool(from_sat), bool(cloudy), float(emissivity),
+           torch.cuda.current_device())
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))          # oldest entry
+        plan = Plan(model, nl, frq, angles, ray_tracing=ray_tracing, from_sat=from_sat, cloudy=cloudy,
+                    tau_layers=False, emissivity=emissivity)
+        _PLAN_CACHE[key] = plan
+    return plan
