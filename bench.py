@@ -36,6 +36,25 @@ WORKLOAD = ("BASELINE.json configs[1]: 10^4 synthetic radiosonde-shaped profiles
             "HATPRO channels x 10 elevations, clear sky, R24, per GPU")
 
 
+_JSON_OUT = None
+
+
+def _reserve_stdout():
+    """Keep the real stdout for the ONE JSON line and point fd 1 at stderr for everything else, so that
+    library chatter written to the C-level stdout (NCCL prints its version banner there) cannot end up
+    beside the JSON line."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def cpu_arm(steps, warmup, budget_s):
     cmd = [sys.executable, "-m", "oracle.cpu_baseline", "--levels", str(LEVELS), "--model", MODEL,
            "--steps", str(steps), "--warmup", str(warmup), "--budget-s", str(budget_s)]
@@ -63,7 +82,7 @@ def run_reference(args):
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 class ClockSampler(threading.Thread):
@@ -130,6 +149,7 @@ def main():
                     help="N>1: 0 = gather of step s overlaps the kernels of step s+1 (default); k>0 = "
                          "within-step overlap over k pieces of the local shard")
     args = ap.parse_args()
+    _reserve_stdout()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -368,7 +388,7 @@ def main():
             "gpu_launches": args.steps * (plan.launch_count(P) * (args.gather_chunks if (N > 1 and args.gather_chunks > 0) else 1)),
             "roofline": roof, "cpu_baseline": cpu, "checksum_tbtotal": checksum,
             "max_abs_dtb_vs_oracle_K": "see tests/test_gpu_parity.py (1e-3 K gate) and profiles/r01_parity.jsonl (measured <= 2e-10 K; absorption <= 1.4e-12 relative)"}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if N > 1:
         dist.destroy_process_group()
 
