@@ -29,7 +29,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inc", ".h"))]
     deps.append(os.path.join(HERE, "..", "include", "mwrt.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 

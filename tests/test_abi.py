@@ -110,3 +110,24 @@ def test_synth_profiles_realism_windows():
 def test_golden_file_is_labelled_unpinned():
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "config1_us_standard.json")))
     assert "NOT PyRTlib" in g["source"]
+
+
+def test_hot_kernel_resource_budget(built_lib):
+    """The occupancy the measured numbers rest on: kernel 1 at 128 registers (4 CTAs/SM) with at most a
+    few spilled words, the plane-parallel kernel 3 at <= 170 registers (3 CTAs/SM) without spills.
+    Read from ptxas -v of the in-tree build (csrc/build.log)."""
+    log = os.path.join(ROOT, "mwr_fast_forward_operators_and_lbls_b200", "csrc", "build.log")
+    if not os.path.exists(log):
+        from mwr_fast_forward_operators_and_lbls_b200 import build
+        build.build(force=True)
+    text = open(log).read()
+
+    def usage(mangled_prefix):
+        m = re.search(r"Compiling entry function '(%s[^']*)'.*?\n.*?\n\s*(\d+) bytes stack frame, (\d+) bytes spill "
+                      r"stores, (\d+) bytes spill loads\n.*?Used (\d+) registers" % re.escape(mangled_prefix), text)
+        assert m, "kernel %s not found in build.log" % mangled_prefix
+        return dict(spill_st=int(m.group(3)), spill_ld=int(m.group(4)), regs=int(m.group(5)))
+    k1 = usage("_ZN4mwrt12k_absorptionILi14EEE")
+    assert k1["regs"] <= 128 and k1["spill_st"] <= 128, k1
+    k3 = usage("_ZN4mwrt5k_rteILi10ELb0ELb1ELb0ELb0EEE")
+    assert k3["regs"] <= 170 and k3["spill_st"] == 0, k3
