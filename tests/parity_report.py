@@ -3,12 +3,12 @@
 PyRTlib is unpinned): max relative error of the absorption coefficients and optical
 depths, max |dTB|, for every model string on synthetic profiles.  Prints one JSON line per model.
 
-    python tools/parity_report.py [P] [L] > profiles/rNN_parity.jsonl
+    python tests/parity_report.py [P] [L] > profiles/rNN_parity.jsonl
 """
 import json
 import os
 import sys
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))   # repo root
 import numpy as np
 import mwr_fast_forward_operators_and_lbls_b200 as pkg
 from oracle import pyrtlib_vec as pv
