@@ -426,9 +426,13 @@ def test_fused_gather_single_rank(pkg):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, MWRT_CHECK_P="777", MWRT_CHECK_NOTIME="1")
+    import socket
     for mode in ("peers", "auto"):
+        with socket.socket() as sk:          # a free port per launch
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "1",
-                            "--master-addr", "127.0.0.1", "--master-port", "29541",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port),
                             os.path.join(root, "tools", "check_fused_gather.py"), mode],
                            capture_output=True, text=True, timeout=300, env=env, cwd=root)
         if r.returncode == 77:
