@@ -3,26 +3,34 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --config 3|4|5                            # another BASELINE config as the headline line
 
 Workload (config.workload): BASELINE.json configs[1] -- 10^4 synthetic radiosonde-shaped profiles
 (100 levels) x 14 HATPRO channels x 10 elevations, clear sky, model R24 (the reference's analysis
 baseline, PyRTlib_processing.py:128-135), PER GPU (weak scaling: profiles shard by rank, the only
-collective is the final all-gather of the results).  One "step" = one pass of the whole path
+exchange is the final gather of the results).  One "step" = one pass of the whole path
 (vapour pressure -> absorption -> slant path -> RTE) over that batch.
 
-  value  device-resident inputs, CUDA-event time summed over the K steps, max over ranks
+  value  device-resident inputs; ONE CUDA-event pair around the K steps (L2 flushes and the tail of the
+         last gather inside it), max over ranks -- the same clock for every N
   e2e    the same batch through the host entry point (mwrt_plan_forward_host): pinned host buffers in,
          host buffers out, H2D and D2H copies inside the timed region
   roofline  dominant kernel = k_absorption, timed alone with CUDA events; fp64-pipe bound, so the
          denominator is a DFMA-stream peak measured in the same run (MEASURED_PEAKS.json has no fp64
          figure); HBM numbers are given beside it
-  cpu_baseline  oracle/cpu_baseline.py (PyRTlib-shaped port, all host cores) on a bounded sample
+  cpu_baseline  oracle/cpu_baseline.py (PyRTlib-shaped port, all host cores) on a bounded sample; the
+         same leg checks the GPU against the oracle on 256 seeded profiles -> max_abs_dtb_vs_oracle_K
+  extra.configs  BASELINE.json configs[2..4] at FULL size, split over the N ranks (strong scaling) and
+         gathered: 10^5 cloudy profiles with 700 sub-frequencies -> 14 channels; the 4001-frequency
+         dense spectrum with per-layer optical depth; 5x10^5 ICON-D2-like columns
+  extra.f32_lineshape  the fp32 line-shape mode, reported separately (north_star: <= 0.01 K)
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -34,6 +42,7 @@ UNIT = "TB/s (brightness temperatures per second)"
 P_PER_GPU, LEVELS, MODEL = 10000, 100, "R24"
 WORKLOAD = ("BASELINE.json configs[1]: 10^4 synthetic radiosonde-shaped profiles (100 levels) x 14 "
             "HATPRO channels x 10 elevations, clear sky, R24, per GPU")
+SIX = ("tbtotal", "tbatm", "tmr", "tauwet", "taudry", "tauliq")   # north_star's six outputs
 
 
 _JSON_OUT = None
@@ -55,9 +64,11 @@ def _emit(line):
     _JSON_OUT.flush()
 
 
-def cpu_arm(steps, warmup, budget_s):
+def cpu_arm(steps, warmup, budget_s, parity_out=""):
     cmd = [sys.executable, "-m", "oracle.cpu_baseline", "--levels", str(LEVELS), "--model", MODEL,
            "--steps", str(steps), "--warmup", str(warmup), "--budget-s", str(budget_s)]
+    if parity_out:
+        cmd += ["--parity-out", parity_out]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("cpu baseline failed: " + r.stderr[-2000:])
@@ -130,6 +141,113 @@ class ClockSampler(threading.Thread):
                 "samples": len(win)}
 
 
+# --------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2..4] at full size, split over the ranks
+# --------------------------------------------------------------------------------------------------
+CONFIG_NAMES = {
+    2: WORKLOAD,
+    3: "BASELINE.json configs[2]: 10^5 profiles with liquid-cloud layers, 14 channels x 50 sub-frequencies "
+       "(700 monochromatic) band-pass averaged to 14, 10 elevations, R24, split over the ranks",
+    4: "BASELINE.json configs[3]: dense spectrum 20-60 GHz at 10 MHz (4001 frequencies) x 10^4 profiles x 150 "
+       "levels, per-layer optical depth (P,F,L) + zenith TB, R24, split over the ranks",
+    5: "BASELINE.json configs[4]: ICON-D2-like domain, 5x10^5 columns x 65 levels x 14 channels x 10 "
+       "elevations, R24, split over the ranks",
+}
+
+
+def build_config(pkg, cfg, rank, world, scale=1.0):
+    """Plan + this rank's shard of configuration `cfg` (profiles split evenly; seed = 1234 + rank)."""
+    import numpy as np
+    from mwr_fast_forward_operators_and_lbls_b200.distributed import shard_range
+    if cfg == 3:
+        Ptot, L, nsub = int(100000 * scale), 100, 50
+        a, b = shard_range(Ptot, rank, world)
+        d = pkg.synth_profiles(b - a, L, seed=1234 + rank, clouds=True)
+        frq, ang = pkg.band_frequencies(nsub), pkg.HATPRO_ELEV
+        plan = pkg.Plan(MODEL, L, frq, ang, cloudy=True, bandpass=(14, nsub, None))
+        fields, kw = SIX, dict(cloudy=True)
+    elif cfg == 4:
+        Ptot, L = int(10000 * scale), 150
+        a, b = shard_range(Ptot, rank, world)
+        d = pkg.synth_profiles(b - a, L, seed=1234 + rank)
+        frq, ang = pkg.dense_spectrum(), np.array([90.0])
+        plan = pkg.Plan(MODEL, L, frq, ang, tau_layers=True)
+        fields, kw = ("tbtotal",), dict(tau_layers=True)
+    elif cfg == 5:
+        Ptot, L = int(500000 * scale), 65
+        a, b = shard_range(Ptot, rank, world)
+        d = pkg.synth_profiles(b - a, L, seed=1234 + rank, top_km=22.0, exponent=2.5, lowest_layer_km=0.02)
+        frq, ang = pkg.HATPRO_FRQ, pkg.HATPRO_ELEV
+        plan = pkg.Plan(MODEL, L, frq, ang)
+        fields, kw = SIX, {}
+    else:
+        raise ValueError(cfg)
+    return dict(plan=plan, d=d, Ptot=Ptot, P=b - a, L=L, F=len(frq), A=len(ang), fields=fields, kw=kw)
+
+
+def run_config(pkg, cfg, rank, world, reps=3, scale=1.0):
+    """One BASELINE configuration at full size over `world` ranks: every rank computes its shard, the
+    (P,Fo,A) results are all-gathered (one NCCL collective of the stacked fields per pass, inside the
+    timing); config 4's 48 GB per-layer optical depth stays sharded (each rank keeps its block).
+    Time = CUDA events around a pass, median of `reps`, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mwr_fast_forward_operators_and_lbls_b200 import roofline
+    c = build_config(pkg, cfg, rank, world, scale)
+    plan, d, fields = c["plan"], c["d"], c["fields"]
+    P, Ptot, L, F, A = c["P"], c["Ptot"], c["L"], c["F"], c["A"]
+    dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    nf, Fo = len(fields), plan.Fo
+    pmax = -(-Ptot // world)
+    stacked = torch.zeros((pmax, nf, Fo, A), dtype=torch.float64, device="cuda")   # padded to the largest shard
+    out = {k: torch.empty((P, Fo, A), dtype=torch.float64, device="cuda") for k in fields}
+    out["status"] = torch.empty((P,), dtype=torch.int32, device="cuda")
+    if c["kw"].get("tau_layers"):
+        out["tau_layer"] = torch.empty((P, F, L), dtype=torch.float64, device="cuda")
+    full = torch.empty((world * pmax, nf, Fo, A), dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def one_pass():
+        plan.forward(dev["z"], dev["p"], dev["t"], dev["rh"], dev.get("denliq"), dev.get("denice"),
+                     fields=fields, out=out)
+        if world > 1:
+            for i, k in enumerate(fields):
+                stacked[:P, i].copy_(out[k])
+            dist.all_gather_into_tensor(full, stacked)
+    ts = []
+    for it in range(1 + reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_pass()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if it > 0:
+            ts.append(float(t.item()))
+    ms = float(np.median(ts))
+    finite = bool(torch.isfinite(out["tbtotal"]).all().item())
+    w = roofline.work(Ptot, L, F, A, cloudy=c["kw"].get("cloudy", False), tau_layers=c["kw"].get("tau_layers", False))
+    res = {"config": CONFIG_NAMES[cfg], "profiles_total": Ptot, "profiles_per_rank": P, "levels": L,
+           "frequencies": F, "channels_out": Fo, "elevations": A, "n_gpus": world, "ms_per_pass": ms,
+           "all_ms": ts, "tb_per_s": Ptot * Fo * A / ms * 1e3, "mono_tb_per_s": Ptot * F * A / ms * 1e3,
+           "algorithmic_tflops": w["flops_total"] / ms / 1e9,
+           "algorithmic_tflops_per_gpu": w["flops_total"] / ms / 1e9 / world,
+           "gathered": "all ranks hold the (P,Fo,A) fields" + ("; tau_layer stays sharded" if cfg == 4 else "")
+                       if world > 1 else "single GPU",
+           "launches_per_pass_per_rank": plan.launch_count(P), "finite": finite}
+    if cfg == 4:
+        res["tau_layer_gbytes"] = 8.0 * Ptot * F * L / 1e9
+        res["tau_layer_gbs"] = 8.0 * Ptot * F * L / ms / 1e6
+    del plan, dev, out, stacked, full
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -137,17 +255,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip extra.configs (BASELINE configs 3/4/5 at full size) and extra.f32_lineshape")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="2 (default): the headline workload, BASELINE.json configs[1]; 3/4/5: print the line "
+                         "of that configuration instead (full size, split over the ranks)")
+    ap.add_argument("--scale", type=float, default=1.0, help="--config 3/4/5 and extras: fraction of the full size")
     ap.add_argument("--model", default=MODEL)
-    ap.add_argument("--gather", default="nccl", choices=["fused", "nccl"],
-                    help="N>1: 'fused' = kernel 3 stores its results straight into every rank's gathered "
-                         "buffer over NVLink (multicast / peer stores, no collective kernel); 'nccl' = "
-                         "all_gather_into_tensor overlapped with the next step")
+    ap.add_argument("--gather", default="ce", choices=["ce", "fused", "nccl"],
+                    help="N>1: 'ce' = every rank pushes its results to each peer with one copy-engine memcpy "
+                         "per peer onto symmetric memory, overlapped with the next step (no collective "
+                         "kernel); 'fused' = kernel 3 stores straight into every rank's buffer over NVLink "
+                         "(multicast / peer stores); 'nccl' = all_gather_into_tensor overlapped with the next step")
     ap.add_argument("--split", type=int, default=1,
                     help="mwrt_plan_set_split: pieces of the device-entry batch (kernel 3 of piece c on a side "
-                         "stream while kernel 1 of piece c+1 runs); spreads the fused gather's stores in time")
-    ap.add_argument("--gather-chunks", type=int, default=0,
-                    help="N>1: 0 = gather of step s overlaps the kernels of step s+1 (default); k>0 = "
-                         "within-step overlap over k pieces of the local shard")
+                         "stream while kernel 1 of piece c+1 runs)")
     args = ap.parse_args()
     _reserve_stdout()
     if args.impl == "reference":
@@ -159,7 +281,7 @@ def main():
     import torch.distributed as dist
     import mwr_fast_forward_operators_and_lbls_b200 as pkg
     from mwr_fast_forward_operators_and_lbls_b200 import _lib, roofline
-    from mwr_fast_forward_operators_and_lbls_b200.distributed import (FusedGatherForward, OverlappedForward,
+    from mwr_fast_forward_operators_and_lbls_b200.distributed import (CopyEngineGather, FusedGatherForward,
                                                                      PipelinedForward)
     from mwr_fast_forward_operators_and_lbls_b200.forward import _ptr, _stream
 
@@ -173,6 +295,19 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N = world
+
+    if args.config != 2:       # another configuration as the line (builder runs; the driver uses the default)
+        r = run_config(pkg, args.config, rank, world, reps=max(3, min(args.steps, 10)), scale=args.scale)
+        if rank == 0:
+            _emit({"metric": METRIC, "value": r["tb_per_s"], "unit": UNIT, "n_gpus": N, "steps": len(r["all_ms"]),
+                   "warmup": 1, "ms_per_step": r["ms_per_pass"], "higher_is_better": True, "scaling": "strong",
+                   "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                   "config": {"workload": r["config"], "scale": args.scale}, "detail": r,
+                   "gpu_launches": len(r["all_ms"]) * r["launches_per_pass_per_rank"] * N})
+        if N > 1:
+            dist.destroy_process_group()
+        return
+
     P, L = P_PER_GPU, LEVELS
     frq, ang = pkg.HATPRO_FRQ, pkg.HATPRO_ELEV
     F, A = len(frq), len(ang)
@@ -183,39 +318,44 @@ def main():
     plan = pkg.Plan(args.model, L, frq, ang)
     if args.split > 1:
         plan.set_split(args.split)
-    fields = ("tbtotal", "tbatm", "tmr", "tauwet", "taudry", "tauliq")   # north_star's six outputs
+    fields = SIX
     out = {k: torch.empty((P, F, A), dtype=torch.float64, device="cuda") for k in fields}
     out["status"] = torch.empty((P,), dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")       # > 126 MB L2
 
-    # N>1: the steps are a stream of batches; the all-gather of step s (six outputs, one collective)
-    # runs on a side stream while step s+1 computes (double-buffered).  --gather-chunks > 0 selects the
-    # within-step form instead (chunk c+1 computed while chunk c travels).
+    # N>1: the steps are a stream of batches; the gather of step s (the fields that carry information +
+    # the status words) travels while step s+1 computes (double-buffered).
     ovl = None
     gather_desc = "none"
     if N > 1:
-        if args.gather_chunks > 0:
-            ovl = OverlappedForward(plan, P, fields, nchunk=args.gather_chunks)
-            gather_desc = ("one all_gather_into_tensor of the six stacked outputs per chunk, %d chunks "
-                           "overlapped within the step" % args.gather_chunks)
-        else:
-            if args.gather == "fused":
-                try:
-                    ovl = FusedGatherForward(plan, P, fields)
-                    gather_desc = ("fused into kernel 3: every rank's RTE kernel stores its results into the "
-                                   "gathered buffer of all ranks over NVLink (%s), one symmetric-memory "
-                                   "barrier per step; no collective kernel" %
-                                   ("multimem.st multicast through NVSwitch" if ovl.mode == "multicast"
-                                    else "one store per peer"))
-                except Exception as exc:      # symmetric memory not available: plain NCCL
-                    if rank == 0:
-                        print("fused gather unavailable (%s); using NCCL" % exc, file=sys.stderr)
-                    ovl = None
-            if ovl is None:
-                ovl = PipelinedForward(plan, P, fields)
-                gather_desc = ("one all_gather_into_tensor of the six stacked outputs per step, overlapped "
-                               "with the next step's kernels (double-buffered); the last step's gather is "
-                               "inside the timed total")
+        if args.gather == "ce":
+            try:
+                ovl = CopyEngineGather(plan, P, fields)
+                gather_desc = ("copy engines: every rank pushes its %d fields (%s; tauliq is identically zero in "
+                               "clear sky and is rebuilt from the gathered status words) to each of the %d peers "
+                               "with ONE cudaMemcpyAsync per peer onto symmetric memory, on side streams, while "
+                               "the next step computes; one symmetric-memory barrier per step; no collective "
+                               "kernel" % (len(ovl.moved), ",".join(ovl.moved), N - 1))
+            except Exception as exc:          # symmetric memory not available: plain NCCL
+                if rank == 0:
+                    print("copy-engine gather unavailable (%r); using NCCL" % (exc,), file=sys.stderr)
+                ovl = None
+        elif args.gather == "fused":
+            try:
+                ovl = FusedGatherForward(plan, P, fields)
+                gather_desc = ("fused into kernel 3: every rank's RTE kernel stores its results into the "
+                               "gathered buffer of all ranks over NVLink (%s), one symmetric-memory "
+                               "barrier per step; no collective kernel" %
+                               ("multimem.st multicast through NVSwitch" if ovl.mode == "multicast"
+                                else "one store per peer"))
+            except Exception as exc:
+                if rank == 0:
+                    print("fused gather unavailable (%r); using NCCL" % (exc,), file=sys.stderr)
+                ovl = None
+        if ovl is None:
+            ovl = PipelinedForward(plan, P, fields)
+            gather_desc = ("one all_gather_into_tensor of the six stacked outputs per step, overlapped "
+                           "with the next step's kernels (double-buffered)")
 
     def step():
         if N > 1:
@@ -234,35 +374,39 @@ def main():
     for _ in range(args.warmup):
         flush.zero_()
         step()
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
-    t_wall0 = time.time()
-    for e0, e1 in ev:
-        flush.zero_()          # L2 flush between timed steps, outside the event pair
-        e0.record()
-        res = step()
-        e1.record()
-    # tail: the last step's gather must have landed before the clock stops
-    tail0, tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    tail0.record()
-    if isinstance(ovl, (PipelinedForward, FusedGatherForward)):
+    if N > 1:
         ovl.finish()
-    tail1.record()
+    barrier()
+    # ONE event pair around the whole timed region -- K steps, the L2 flush before each of them and the
+    # tail of the last gather -- for every N, so that nothing runs un-timed between steps
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    t_begin.record()
+    for _ in range(args.steps):
+        flush.zero_()          # L2 flush between timed steps (inside the timed region)
+        res = step()
+    if N > 1:
+        ovl.finish()           # the last step's gather must have landed before the clock stops
+    t_end.record()
     barrier()
     t_wall1 = time.time()
-    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev] + [tail0.elapsed_time(tail1)]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    total_ms = torch.tensor([t_begin.elapsed_time(t_end)], dtype=torch.float64, device="cuda")
     if N > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     value = N * P * F * A * args.steps / (total_ms * 1e-3)
-    if isinstance(ovl, (PipelinedForward, FusedGatherForward)):
+    if N > 1:
         checksum = float(ovl.field("tbtotal", res).sum().item())
-    elif N > 1:
-        checksum = float(res.field("tbtotal").sum().item())
     else:
         checksum = float(res["tbtotal"].sum().item())
+    # what the flushes cost inside the timed region (reported, not subtracted)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(20):
+        flush.zero_()
+    f1.record()
+    torch.cuda.synchronize()
+    flush_ms = f0.elapsed_time(f1) / 20
 
     # ---- end to end through the host entry point (pinned host memory, copies inside the timing)
     hin = pkg.pinned_fields(keys, d[keys[0]].shape)     # one pinned block per direction: the library
@@ -299,9 +443,8 @@ def main():
     if N > 1:
         dist.all_reduce(e2e1_s, op=dist.ReduceOp.MAX)
     e2e1_value = N * P * F * A * e2e_steps / float(e2e1_s.item())
-    t_wall2 = time.time()
 
-    # ---- dominant kernel alone (k_absorption) for the roofline
+    # ---- dominant kernel alone (k_absorption) for the roofline, fp64 and fp32 line-shape mode
     lib = _lib.load()
     m = pkg.get_model(args.model)
     e_t = pkg.vapor(dev["t"], dev["rh"])[0]
@@ -309,23 +452,24 @@ def main():
     awet = torch.empty((P, F, L), dtype=torch.float64, device="cuda")
     adry = torch.empty_like(awet)
 
-    def k_abs():
-        _lib.check(lib.mwrt_absorption_f64(m.handle, P, L, F, _ptr(dev["p"]), _ptr(dev["t"]), _ptr(e_t),
-                                           None, None, _ptr(f_t), _ptr(awet), _ptr(adry), None, None,
-                                           None, _stream()), "absorption")
-    for _ in range(3):
-        k_abs()
-    torch.cuda.synchronize()
-    kt = []
-    for _ in range(max(5, min(args.steps, 30))):
-        flush.zero_()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        k_abs()
-        a1.record()
+    def time_abs(fn_c):
+        def k_abs():
+            _lib.check(fn_c(m.handle, P, L, F, _ptr(dev["p"]), _ptr(dev["t"]), _ptr(e_t), None, None,
+                            _ptr(f_t), _ptr(awet), _ptr(adry), None, None, None, _stream()), "absorption")
+        for _ in range(3):
+            k_abs()
         torch.cuda.synchronize()
-        kt.append(a0.elapsed_time(a1))
-    k_ms = sum(kt) / len(kt)
+        kt = []
+        for _ in range(max(5, min(args.steps, 30))):
+            flush.zero_()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            k_abs()
+            a1.record()
+            torch.cuda.synchronize()
+            kt.append(a0.elapsed_time(a1))
+        return sum(kt) / len(kt)
+    k_ms = time_abs(lib.mwrt_absorption_f64)
     sampler.stop()
     desc = pkg.load_descriptor(args.model)
     w = roofline.work(P, L, F, A, n_h2o=len(desc["h2o"]["fl"]), n_o2=len(desc["o2"]["f"]))
@@ -336,45 +480,107 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    traffic = None   # measured DRAM bytes per launch from the committed ncu --set full capture
-    try:
-        if args.model == MODEL:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_absorption"]["traffic_bytes"]
-    except Exception:
-        pass
+    traffic, traffic_src = None, None   # measured DRAM bytes per launch from the committed ncu --set full capture
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            if args.model == MODEL:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", name)))["k_absorption"]["traffic_bytes"]
+                traffic_src = "profiles/" + name
+                break
+        except Exception:
+            pass
+    step_ms = total_ms / args.steps
     roof = {"bound": "fp64", "kernel": "k_absorption", "achieved": achieved,
             "peak": peak_flops / 1e12, "unit": "TFLOP/s", "frac": achieved / (peak_flops / 1e12),
             "peak_source": "self-measured DFMA stream in this run (nominal 37.2); MEASURED_PEAKS.json "
                            "has no fp64 figure",
-            "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r01_traffic.json)",
+            "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, %s)" % traffic_src,
             "kernel_ms": k_ms,
-            "kernel_share_of_step": k_ms / (total_ms / args.steps),
+            "kernel_share_of_step": k_ms / (step_ms - flush_ms),
             "algorithmic_flops_per_launch": w["flops_k_abs"],
             "hbm": {"algorithmic_bytes_per_launch": w["bytes_k_abs"],
                     "achieved_gbs": w["bytes_k_abs"] / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
-            "whole_step_tflops": w["flops_total"] / (total_ms / args.steps * 1e-3) / 1e12}
+            "whole_step_tflops": w["flops_total"] / ((step_ms - flush_ms) * 1e-3) / 1e12}
+
+    # ---- extras: fp32 line-shape mode (reported separately) and BASELINE configs 3/4/5 at full size
+    extra = {}
+    if not args.no_extras:
+        k32_ms = time_abs(lib.mwrt_absorption_f32ls)
+        plan32 = pkg.Plan(args.model, L, frq, ang, f32_lineshape=True)
+        out32 = {k: torch.empty((P, F, A), dtype=torch.float64, device="cuda") for k in fields}
+        out32["status"] = torch.empty((P,), dtype=torch.int32, device="cuda")
+        o64 = plan.forward(dev["z"], dev["p"], dev["t"], dev["rh"], fields=fields, out=out)
+        for _ in range(3):
+            plan32.forward(dev["z"], dev["p"], dev["t"], dev["rh"], fields=fields, out=out32)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n32 = max(5, min(args.steps, 30))
+        g0.record()
+        for _ in range(n32):
+            flush.zero_()
+            plan32.forward(dev["z"], dev["p"], dev["t"], dev["rh"], fields=fields, out=out32)
+        g1.record()
+        torch.cuda.synchronize()
+        ms32 = g0.elapsed_time(g1) / n32
+        dtb = float((out32["tbtotal"] - o64["tbtotal"]).abs().max().item())
+        dtau = float(((out32["taudry"] + out32["tauwet"]) / (o64["taudry"] + o64["tauwet"]) - 1).abs().max().item())
+        extra["f32_lineshape"] = {
+            "what": "fp32 line-shape mode (mwrt_plan_set_precision / mwrt_absorption_f32ls): the pair loops of "
+                    "kernel 1 on the FP32 pipe, everything else fp64; same workload as the headline line",
+            "ms_per_step": ms32, "value": P * F * A / (ms32 * 1e-3), "unit": UNIT,
+            "k_absorption_ms": k32_ms, "k_absorption_ms_fp64": k_ms,
+            "max_abs_dtb_vs_fp64_path_K": dtb, "max_rel_dtau_vs_fp64_path": dtau, "gate_K": 0.01,
+            "timing": "one CUDA-event pair around %d steps, L2 flush inside" % n32}
+        del plan32, out32
+        cfgs = []
+        for cfg in (3, 5, 4):
+            try:
+                cfgs.append(run_config(pkg, cfg, rank, world, reps=3, scale=args.scale))
+            except Exception as exc:      # e.g. out of memory on a smaller part: say so, keep the line
+                cfgs.append({"config": CONFIG_NAMES[cfg], "error": repr(exc)})
+                torch.cuda.empty_cache()
+        extra["configs"] = cfgs
 
     if rank != 0:
         if N > 1:
             dist.destroy_process_group()
         return
     clocks = sampler.summary(t_wall0, t_wall1)
-    cpu = None
-    if N == 1 and not args.no_cpu_baseline:
-        c = cpu_arm(1, 0, budget_s=15.0)
-        cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
-               "sample": c["sample"], "s_per_execute": c["s_per_execute"]}
+    # ---- cpu_baseline leg: the PyRTlib-shaped port timed on the host cores (N=1 only) and the oracle as
+    # the CHECKER of this run's GPU results on 256 seeded profiles (outside every timed region)
+    cpu, parity = None, None
+    if not args.no_cpu_baseline:
+        with tempfile.TemporaryDirectory() as tmp:
+            pfile = os.path.join(tmp, "parity.npz")
+            if N == 1:
+                c = cpu_arm(1, 0, budget_s=15.0, parity_out=pfile)
+                cpu = {"value": c["value"], "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
+                       "sample": c["sample"], "s_per_execute": c["s_per_execute"]}
+            else:
+                cpu_arm(1, 0, budget_s=0.5, parity_out=pfile)
+            ref = np.load(pfile)
+            dp = pkg.synth_profiles(int(ref["nprof"]), int(ref["levels"]), seed=int(ref["seed"]))
+            got = pkg.simulate(dp["z"], dp["p"], dp["t"], dp["rh"], frq, ang, args.model)
+            parity = {"profiles": int(ref["nprof"]),
+                      "max_abs_dtb_K": {k: float(np.max(np.abs(got[k].cpu().numpy() - ref[k])))
+                                        for k in ("tbtotal", "tbatm", "tmr")},
+                      "max_rel_dtau": {k: float(np.max(np.abs(got[k].cpu().numpy() / ref[k] - 1.0)))
+                                       for k in ("tauwet", "taudry")},
+                      "oracle": "oracle/pyrtlib_vec.py (in-repo restatement; parity with real PyRTlib unpinned)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "model": args.model, "profiles_per_gpu": P, "levels": L,
                        "channels": F, "elevations": A, "parallelism": "profiles sharded by rank (dp%d)" % N,
                        "outputs": list(fields),
                        "collective": gather_desc,
-                       "l2": "256 MiB flush between timed steps, outside the CUDA-event pairs",
-                       "timing": "sum of per-step CUDA-event intervals, max over ranks"},
+                       "l2": "256 MiB flush before every timed step, INSIDE the timed region "
+                             "(%.3f ms per flush measured separately, not subtracted)" % flush_ms,
+                       "timing": "one CUDA-event pair around all K steps incl. flushes and the tail of the last "
+                                 "gather, max over ranks"},
             "clocks": clocks,
+            "flush_ms_per_step": flush_ms,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "Plan.forward_host -> mwrt_plan_forward_host (pinned host buffers)",
@@ -385,9 +591,10 @@ def main():
                                      "d2h_bytes_per_step": 8 * P * F * A + 4 * P,
                                      "note": "same call asking for `tbtotal` alone, the one column the "
                                              "reference's driver reads (PyRTlib_processing.py:127)"}},
-            "gpu_launches": args.steps * (plan.launch_count(P) * (args.gather_chunks if (N > 1 and args.gather_chunks > 0) else 1)),
+            "gpu_launches": args.steps * plan.launch_count(P),
             "roofline": roof, "cpu_baseline": cpu, "checksum_tbtotal": checksum,
-            "max_abs_dtb_vs_oracle_K": "see tests/test_gpu_parity.py (1e-3 K gate) and profiles/r01_parity.jsonl (measured <= 2e-10 K; absorption <= 1.4e-12 relative)"}
+            "max_abs_dtb_vs_oracle_K": None if parity is None else parity["max_abs_dtb_K"]["tbtotal"],
+            "parity": parity, "extra": extra}
     _emit(line)
     if N > 1:
         dist.destroy_process_group()

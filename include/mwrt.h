@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MWRT_VERSION 100 /* 0.1.0 */
+#define MWRT_VERSION 200 /* 0.2.0: mwrt_profiles / mwrt_outputs grew (cloud levels, tmrcld); fp32 line-shape mode */
 
 /* error codes (negative) */
 #define MWRT_E_ARG (-1)      /* null pointer / non-positive size / bad flag */
@@ -116,6 +116,14 @@ int mwrt_absorption_f64(const mwrt_model* m, int P, int L, int F, const double* 
                         const double* e, const double* denliq, const double* denice, const double* frq,
                         double* awet, double* adry, double* aliq, double* aice, int32_t* status,
                         void* stream);
+/* Same call in the fp32 LINE-SHAPE mode (BASELINE.json north_star: "any fp32 line-shape mode must stay
+ * within 0.01 K and is reported separately"): the per-(line, frequency) Van Vleck-Weisskopf sums run on
+ * the FP32 pipe; line parameters per (level, line), continua, the speed-dependent / narrow-line
+ * corrections and every output stay fp64.  Not PyRTlib-exact: relative error of awet/adry ~1e-6. */
+int mwrt_absorption_f32ls(const mwrt_model* m, int P, int L, int F, const double* p, const double* tk,
+                          const double* e, const double* denliq, const double* denice, const double* frq,
+                          double* awet, double* adry, double* aliq, double* aice, int32_t* status,
+                          void* stream);
 
 /* Slant path length per layer, ds (P,A,L), ds[...,0] = 0.  ray_tracing = 0: diff(z)/sin(elev)
  * (what the reference runs: the 6-argument constructor keeps ray_tracing=False); 1: RTEquation.refractivity
@@ -151,6 +159,11 @@ int mwrt_plan_create(const mwrt_model* m, int L, int F, int A, const double* frq
                      int flags, int chunk_profiles, mwrt_plan** out);
 int mwrt_plan_destroy(mwrt_plan* plan);
 int mwrt_plan_set_emissivity(mwrt_plan* plan, double es);
+/* arithmetic of kernel 1's line sums: MWRT_PREC_F64 (default; the parity path) or
+ * MWRT_PREC_F32_LINESHAPE (see mwrt_absorption_f32ls; TB within 0.01 K of the fp64 path) */
+#define MWRT_PREC_F64 0
+#define MWRT_PREC_F32_LINESHAPE 1
+int mwrt_plan_set_precision(mwrt_plan* plan, int precision);
 /* pieces > 1: mwrt_plan_forward_device cuts the batch into `pieces` parts and overlaps kernel 3 of
  * part c (on a stream owned by the plan) with kernel 1 of part c+1 (on the caller's stream); the
  * caller's stream still completes after everything.  The host entry point runs equal chunks of ~1000
@@ -171,19 +184,35 @@ int mwrt_plan_set_split(mwrt_plan* plan, int pieces);
 #define MWRT_OUT_PEERS 2
 #define MWRT_MAX_PEERS 16
 int mwrt_plan_set_output_fanout(mwrt_plan* plan, int mode, int npeer, const int64_t* peer_byte_offsets);
+/* Multi-GPU gather on the COPY ENGINES (the default of bench.py --gpus N): one asynchronous
+ * device-to-device copy of `bytes` from `src` (this GPU) to `dst` -- a peer GPU's buffer mapped into this
+ * process (symmetric memory / cudaIpc / cuMemMap) -- on `stream`.  A rank pushes its finished (P,F,A)
+ * fields to each peer with one such call per peer on a side stream while the next batch computes; no SM
+ * runs a collective kernel.  (One plain cudaMemcpyAsync per copy: the batched-memcpy entry points of
+ * CUDA 12.8+ are deliberately not used.) */
+int mwrt_push_async(void* dst, const void* src, int64_t bytes, void* stream);
 /* optional band-pass: C channels x S sub-frequencies (C*S == F), host weights (C,S) or NULL = 1/S.
- * Outputs of the forward calls become (P,C,A). */
+ * Outputs of the forward calls become (P,C,A).  The average is taken INSIDE kernel 3 (fixed summation
+ * order, bit-identical to mwrt_bandpass_f64 on the monochromatic fields) whenever a channel's S
+ * sub-frequencies fit one CTA (S <= 384), the path is plane-parallel and the stores are plain;
+ * otherwise the plan falls back to monochromatic fields + mwrt_bandpass_f64. */
 int mwrt_plan_set_bandpass(mwrt_plan* plan, int C, int S, const double* weights);
 /* number of kernels the plan launches for P profiles (bench.py reports it as gpu_launches) */
 int mwrt_plan_launch_count(const mwrt_plan* plan, int P);
 
 typedef struct mwrt_profiles { /* (P,L) each; denliq/denice may be NULL unless MWRT_F_CLOUDY */
   const double *z, *p, *tk, *rh, *denliq, *denice;
+  /* (P,) level indices of the base and top of the first cloud layer (what TbCloudRTE.init_cloudy's
+   * `cldh` selects), -1 = none; only read when mwrt_outputs.tmrcld is asked for; may be NULL */
+  const int32_t *cld_ibase, *cld_itop;
 } mwrt_profiles;
 typedef struct mwrt_outputs { /* (P,F,A) each [(P,C,A) with band-pass]; any may be NULL */
   double *tbtotal, *tbatm, *tmr, *tauwet, *taudry, *tauliq, *tauice;
   double* tau_layer; /* (P,F,L) total layer optical depth at angle 0, needs MWRT_F_TAU_LAYERS */
   int32_t* status;   /* (P,) */
+  /* (P,F,A) mean radiating temperature of the first cloud layer (column `tmrcld` of upstream's
+   * DataFrame; 0 where there is no cloud).  Device entry point, downwelling, no band-pass. */
+  double* tmrcld;
 } mwrt_outputs;
 
 /* device pointers in, device pointers out; asynchronous on `stream` */
@@ -235,16 +264,18 @@ int mwrt_cloud_features_f64(int S, int L, const double* p, const double* t, cons
  * figure).  Synchronises. */
 int mwrt_measure_dfma_peak(double* flops_per_s, double* sm_clock_mhz_est);
 
-/* ---- test helper: the device math helpers the kernels are built from (branch-free exp/log with and
- * without tables, MUFU+Newton reciprocal), evaluated elementwise so tests can check them against
+/* ---- test helper: the device math helpers the kernels are built from (table-driven branch-free
+ * exp/log, MUFU+Newton reciprocal, branch-free atan2), evaluated elementwise so tests can check them against
  * libm.  x, y: device, n doubles.  Domain as documented in csrc/mwrt_common.cuh. */
-#define MWRT_MATH_EXP_NB 0
 #define MWRT_MATH_EXP_TB 1
-#define MWRT_MATH_LOG_NB 2
 #define MWRT_MATH_LOG_TB 3
 #define MWRT_MATH_RCP 4
 #define MWRT_MATH_RCP_SEED 5 /* raw MUFU.RCP64H */
 #define MWRT_MATH_RCP_NR1 6  /* seed + one quadratic Newton step */
+#define MWRT_MATH_ATAN2_X1 7 /* atan2_nb(x, 1)  */
+#define MWRT_MATH_ATAN2_XM1 8 /* atan2_nb(x, -1) */
+#define MWRT_MATH_ATAN2_1X 9 /* atan2_nb(1, x)  */
+#define MWRT_MATH_ATAN2_M1X 10 /* atan2_nb(-1, x) */
 int mwrt_math_selftest_f64(int op, int64_t n, const double* x, double* y, void* stream);
 
 #ifdef __cplusplus

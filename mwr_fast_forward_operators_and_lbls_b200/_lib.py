@@ -14,6 +14,7 @@ O2_COLS = ("f", "s300", "be", "w300", "y0", "y1", "g0", "g1", "dnu0", "dnu1")
 ST_NAN_INPUT, ST_NEG_ABS, ST_DUCTING, ST_RANGE = 1, 2, 4, 8
 F_RAY_TRACING, F_FROM_SAT, F_CLOUDY, F_TAU_LAYERS = 1, 2, 4, 8
 E_ARG, E_MODEL, E_NOMEM, E_STATE = -1, -2, -3, -4
+PREC_F64, PREC_F32_LINESHAPE = 0, 1
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
@@ -31,12 +32,12 @@ class ModelDesc(C.Structure):
 
 
 class Profiles(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("z", "p", "tk", "rh", "denliq", "denice")]
+    _fields_ = [(n, C.c_void_p) for n in ("z", "p", "tk", "rh", "denliq", "denice", "cld_ibase", "cld_itop")]
 
 
 class Outputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("tbtotal", "tbatm", "tmr", "tauwet", "taudry", "tauliq",
-                                          "tauice", "tau_layer", "status")]
+                                          "tauice", "tau_layer", "status", "tmrcld")]
 
 
 # every symbol include/mwrt.h declares (tests/test_abi.py checks the .so exports all of them)
@@ -53,6 +54,7 @@ SYMBOLS = {
     "mwrt_model_destroy": (C.c_int, [C.c_void_p]),
     "mwrt_vapor_f64": (C.c_int, [C.c_int64] + [C.c_void_p] * 5),
     "mwrt_absorption_f64": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 12),
+    "mwrt_absorption_f32ls": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 12),
     "mwrt_slant_path_f64": (C.c_int, [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5
                             + [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mwrt_rte_f64": (C.c_int, [C.c_int] * 4 + [C.c_void_p] * 7 + [C.c_int, C.c_double]
@@ -62,6 +64,7 @@ SYMBOLS = {
                                    C.POINTER(C.c_void_p)]),
     "mwrt_plan_destroy": (C.c_int, [C.c_void_p]),
     "mwrt_plan_set_emissivity": (C.c_int, [C.c_void_p, C.c_double]),
+    "mwrt_plan_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
     "mwrt_plan_set_split": (C.c_int, [C.c_void_p, C.c_int]),
     "mwrt_plan_set_bandpass": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp]),
     "mwrt_plan_launch_count": (C.c_int, [C.c_void_p, C.c_int]),
@@ -69,6 +72,7 @@ SYMBOLS = {
                                            C.POINTER(Outputs), C.c_void_p]),
     "mwrt_plan_forward_host": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Profiles),
                                          C.POINTER(Outputs)]),
+    "mwrt_push_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "mwrt_plan_set_output_fanout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "mwrt_stats_f64": (C.c_int, [C.c_int, C.c_int64] + [C.c_void_p] * 7),
     "mwrt_thin_mean_f64": (C.c_int, [C.c_int] * 3 + [C.c_void_p] * 12),

@@ -2,8 +2,9 @@
 //
 // Replaces, for a whole batch at once, what PyRTlib does inside TbCloudRTE.execute() per
 // (angle, frequency, level): RTEquation.clearsky_absorption -> H2OAbsModel.h2o_absorption,
-// O2AbsModel.o2_absorption, N2AbsModel.n2_absorption, and RTEquation.cloudy_absorption ->
-// LiqAbsModel.liquid_water_absorption (SURVEY.md 8(a) rows 8,10,13; Appendix A.2-A.7).  The reference
+// O2AbsModel.o2_absorption, N2AbsModel.n2_absorption (SURVEY.md 8(a) rows 8,10; Appendix A.2-A.6).
+// Cloud liquid/ice (row 13, A.7) is NOT here: on the fused path kernel 3 evaluates it inline for the
+// cloudy levels (mwrt_cloud.cuh); the stage entry point uses the elementwise k_cloud_abs below.  The reference
 // reaches it through `rte.execute()` at /root/reference/python_src/proc/PyRTlib_processing.py:126.
 //
 // Mapping (B200-first, not PyRTlib's loop order):
@@ -20,6 +21,7 @@
 // Absorption does not depend on the viewing angle: it is computed once and reused for all angles
 // (PyRTlib recomputes it per angle).
 #include "mwrt_common.cuh"
+#include "mwrt_cloud.cuh"
 #include <stdlib.h>
 
 namespace mwrt {
@@ -37,6 +39,11 @@ constexpr int kAllIn = 0, kAllOut = 1, kWing1Out = 2, kMixed = 3;
 __device__ __forceinline__ cplx cdiv_f(cplx a, cplx b) {
   const double r = rcp_fast(fma(b.re, b.re, b.im * b.im));
   return cplx{fma(a.re, b.re, a.im * b.im) * r, fma(a.im, b.re, -a.re * b.im) * r};
+}
+__device__ __forceinline__ float rcp_f32(float x) {   // MUFU.RCP, ~1 ulp (fp32 line-shape mode)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ double sqrt_f(double x) {  // x > 0, normal
   double y;
@@ -174,60 +181,6 @@ __device__ __noinline__ double o2_sd118_sf1(double df, double d1, double y) {
   const cplx one_m = cmake(2.0 * (1.0 - pxw.re), -2.0 * pxw.im);
   return cmul(cmake(1.0, y), one_m).re * rw2;
 }
-// Rayleigh liquid-water absorption per unit density [Np km^-1 / (g m^-3)], split into
-// the temperature-only part (once per level-point) and the per-frequency part.
-struct LiqPrep {
-  // Liebe-91 double Debye: eps0 - eps1, eps1 - eps2, eps2, fp, fs
-  // Rosenkranz-15 (dilec12): kap0, delta, sd, deltb, hdelta, then z1, z2 and 1/cnorm as complex numbers
-  double a, b, c, d, e;
-  cplx z1, icn;
-};
-__device__ __noinline__ LiqPrep liq_prepare(int liq_model, double tk) {
-  LiqPrep q;
-  q.z1 = cmake(0.0, 0.0);
-  q.icn = cmake(0.0, 0.0);
-  if (liq_model == 0) {
-    const double theta1 = 1.0 - 300.0 / tk;
-    const double eps0 = 77.66 - 103.3 * theta1;
-    const double eps1 = 0.0671 * eps0;
-    const double eps2 = 3.52;
-    const double fp = (316.0 * theta1 + 146.4) * theta1 + 20.2;
-    q.a = eps0 - eps1; q.b = eps1 - eps2; q.c = eps2; q.d = fp; q.e = 39.8 * fp;
-  } else {
-    const double tc = tk - 273.15;
-    const double theta = 300.0 / tk;
-    const double lnth = log(theta);
-    q.a = -43.7527 * exp(0.05 * lnth) + 299.504 * exp(1.47 * lnth) - 399.364 * exp(2.11 * lnth) +
-          221.327 * exp(2.31 * lnth);
-    q.b = 80.69715 * exp(-tc / 226.45);
-    q.c = 1164.023 * exp(-651.4728 / (tc + 133.07));
-    q.d = 4.008724 * exp(-tc / 103.05);
-    q.e = q.d / 2.0;
-    const double f1 = 10.46012 + 0.1454962 * tc + 0.063267156 * (tc * tc) + 0.00093786645 * (tc * tc * tc);
-    q.z1 = cmake(-0.75 * f1, f1);
-    const cplx cnorm = clog_(cdiv(cmake(-4500.0, 2000.0), q.z1));
-    q.icn = cnorm;   // kept as cnorm: the oracle divides by it (and by its conjugate)
-  }
-  return q;
-}
-__device__ __noinline__ double liq_abs_eval(int liq_model, const LiqPrep& q, double f) {
-  cplx eps;
-  if (liq_model == 0) {
-    eps = cadd(cdiv(cmake(q.a, 0.0), cmake(1.0, f / q.d)), cdiv(cmake(q.b, 0.0), cmake(1.0, f / q.e)));
-    eps.re += q.c;
-  } else {
-    const cplx z2 = cmake(-4500.0, 2000.0);
-    const cplx z = cmake(0.0, f);
-    cplx kappa = cmake(q.a, 0.0);
-    kappa = csub(kappa, cdiv(cscale(z, q.b), cmake(q.c, f)));
-    const cplx chip = cdiv(cscale(clog_(cdiv(csub(z, z2), csub(z, q.z1))), q.e), q.icn);
-    const cplx chij = cdiv(cscale(clog_(cdiv(csub(z, cconj(z2)), csub(z, cconj(q.z1)))), q.e), cconj(q.icn));
-    eps = cadd(kappa, cmake(chip.re + chij.re - q.d, chip.im + chij.im));
-  }
-  const cplx re = cdiv(cmake(eps.re - 1.0, eps.im), cmake(eps.re + 2.0, eps.im));
-  return -0.06286 * re.im * f;
-}
-
 // frequency-independent state of one H2O / O2 line at one level-point
 // Fast pair form used by both species.  With u = f^2, fc = line centre, w = half width:
 //   D1 D2 = ((f-fc)^2 + w^2)((f+fc)^2 + w^2) = (u - fc^2 + w^2)^2 + 4 fc^2 w^2 = vv^2 + c4,  vv = u - c3
@@ -241,14 +194,74 @@ __device__ __noinline__ double liq_abs_eval(int liq_model, const LiqPrep& q, dou
 // both narrower than 1e-3*fc and closer than 1e-3*fc to a frequency of the block get the exact
 // per-wing form as a correction in the slow-path loop.
 struct H2OLine {
-  double w, wsq, base, shift, sp, w2, dl2, c3, c4, n1, n0;
+  double w, wsq, base, shift, sp, w2, dl2, c3, c4, n1, n0, b32;   // b32 = c3 - fl^2 (fp32 mode)
 };
 struct O2Line {
-  double fcen, df, df2, sp, y, gfac, c3, c4, n1, n0;
+  double fcen, df, df2, sp, y, gfac, c3, c4, n1, n0, b32;        // b32 = c3 - f_k^2
 };
 struct PairHot {   // what the pair loop keeps live: 8 doubles
   double c3a, c4a, n1a, n0a, c3b, c4b, n1b, n0b;
 };
+
+// The innermost loop of kernel 1: one line PAIR against the FB frequencies of the block (see the
+// derivation above H2OLine).  Written stage by stage over groups of G frequencies with ordered FP64 ops
+// (MWRT_FMA & co., mwrt_common.cuh): left to itself the compiler software-pipelines only two
+// frequencies deep, so a warp sits on the MUFU.RCP64H latency and on back-to-back dependent DFMAs
+// (profiles/r01m: `wait` 2.2 and `short_scoreboard` 0.7 warps per issue); with G chains in flight per
+// warp the G reciprocal seeds are issued together and every later stage finds its operands ready.
+#ifndef MWRT_ABS_GROUP
+#define MWRT_ABS_GROUP 7
+#endif
+template <int FB, int G>
+__device__ __forceinline__ void pair_accumulate(double (&acc)[FB], const double2* __restrict__ fsq2,
+                                                const PairHot& h) {
+#if MWRT_ABS_GROUP == 0   // reference form: one frequency after the other, scheduling left to the compiler
+#pragma unroll
+  for (int j = 0; j < FB; ++j) {
+    const double u = (j & 1) ? fsq2[j >> 1].y : fsq2[j >> 1].x;
+    const double va = u - h.c3a, vb = u - h.c3b;
+    const double Da = fma(va, va, h.c4a), Db = fma(vb, vb, h.c4b);
+    const double na = fma(h.n1a, va, h.n0a), nb = fma(h.n1b, vb, h.n0b);
+    const double num = fma(nb, Da, na * Db);
+    acc[j] = fma(num, rcp_nr1(Da * Db), acc[j]);
+  }
+  return;
+#endif
+#pragma unroll
+  for (int j0 = 0; j0 < FB; j0 += G) {
+    double va[G], vb[G], Da[G], Db[G], na[G], nb[G], pr[G], r[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      const int j = (j0 + q < FB) ? j0 + q : FB - 1;
+      const double u = (j & 1) ? fsq2[j >> 1].y : fsq2[j >> 1].x;   // LDS.128: two frequencies per load
+      MWRT_ADD(va[q], u, -h.c3a);
+      MWRT_ADD(vb[q], u, -h.c3b);
+    }
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      MWRT_FMA(Da[q], va[q], va[q], h.c4a);
+      MWRT_FMA(Db[q], vb[q], vb[q], h.c4b);
+      MWRT_FMA(na[q], h.n1a, va[q], h.n0a);
+      MWRT_FMA(nb[q], h.n1b, vb[q], h.n0b);
+    }
+#pragma unroll
+    for (int q = 0; q < G; ++q) {
+      MWRT_MUL(pr[q], Da[q], Db[q]);
+      MWRT_MUL(na[q], na[q], Db[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < G; ++q) asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[q]) : "d"(pr[q]));
+#pragma unroll
+    for (int q = 0; q < G; ++q) MWRT_FMA(nb[q], nb[q], Da[q], na[q]);     // numerator
+#pragma unroll
+    for (int q = 0; q < G; ++q) MWRT_FMA(pr[q], -pr[q], r[q], 1.0);       // Newton residual
+#pragma unroll
+    for (int q = 0; q < G; ++q) MWRT_FMA(r[q], r[q], pr[q], r[q]);        // rcp_nr1
+#pragma unroll
+    for (int q = 0; q < G; ++q)
+      if (j0 + q < FB) MWRT_FMA(acc[j0 + q], nb[q], r[q], acc[j0 + q]);
+  }
+}
 
 // shared-memory line tables are LINE-major (one row per line, read with LDS.128 at immediate
 // offsets): the model's columns, then 1/f_line^2, padded to an even stride
@@ -264,15 +277,26 @@ __host__ __device__ inline int abs_smem_doubles(int nh, int no, int FB) {
 #ifndef MWRT_ABS_MINB
 #define MWRT_ABS_MINB 4
 #endif
-template <int FB>
+#ifndef MWRT_ABS_WIDE_DEFAULT
+#define MWRT_ABS_WIDE_DEFAULT 1
+#endif
+// F32 = fp32 line-shape mode (mwrt_plan_set_precision): the two innermost pair loops run on the FP32
+// pipe; everything hoisted per (level-point, line), the corrections (speed dependence, narrow lines),
+// the continua and the accumulation across lines stay fp64.  To keep the one cancellation of the pair
+// form out of fp32, vv = f^2 - c3 is formed as (f^2 - fl^2) - (c3 - fl^2): the first difference is
+// tabulated per CTA in fp64 and rounded once, the second is a small per-line quantity.  Strengths are
+// scaled by 2^40 so that no term comes near the fp32 denormal range (undone exactly at the end).
+constexpr double kF32Scale = 1099511627776.0, kF32Unscale = 1.0 / 1099511627776.0;   // 2^40
+struct PairHotF {
+  float ba, c4a, n1a, n0a, bb, c4b, n1b, n0b;
+};
+template <int FB, bool F32>
 __global__ void __launch_bounds__(kAbsThreads, FB > 16 ? 3 : MWRT_ABS_MINB)
 k_absorption(const ModelDev m, const long long npts, const int L, const int F, const int nfb,
              const double* __restrict__ p_in, const double* __restrict__ tk_in,
              const double* __restrict__ e_in, const int e_is_rh, double* __restrict__ e_out,
-             double* __restrict__ rho_out, const double* __restrict__ denliq,
-             const double* __restrict__ denice, const double* __restrict__ frq,
-             double* __restrict__ awet, double* __restrict__ adry, double* __restrict__ aliq,
-             double* __restrict__ aice, int* __restrict__ status) {
+             double* __restrict__ rho_out, const double* __restrict__ frq,
+             double* __restrict__ awet, double* __restrict__ adry, int* __restrict__ status) {
   extern __shared__ __align__(16) double smem[];
   const int nh = m.n_h2o, no = m.n_o2;
   const int nop = (no + 1) & ~1;          // O2 lines padded to an even count (dummy: strength 0)
@@ -289,6 +313,9 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
   int* cnt = hord + nh;                   // [0] all-in lines, [1] lines that contribute at all
   int* hchk = cnt + 2;                    // nh: can this line need a correction in this block at all?
   int* ochk = hchk + nh;                  // nop: same for the O2 lines
+  // fp32 line-shape mode: (f_j^2 - f_line^2) rounded to fp32, nh x FB then nop x FB
+  float* a32h = reinterpret_cast<float*>(smem + abs_smem_doubles(nh, no, FB));
+  float* a32o = a32h + nh * FB;
   __shared__ double etab[kExpTabN];             // exp_tb / log_tb tables (mwrt_common.cuh)
   __shared__ __align__(16) double ltab[128];
   exp_tab_stage(etab);
@@ -328,6 +355,16 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
       double fl = hrow[(i / FB) * kHS + MWRT_H2O_FL], f = fblk[i % FB];
       dfm[i] = f - fl;
       dfp[i] = f + fl;
+    }
+    if (F32) {
+      for (int i = threadIdx.x; i < nh * FB; i += blockDim.x) {
+        const double fl = hrow[(i / FB) * kHS + MWRT_H2O_FL], f = fblk[i % FB];
+        a32h[i] = (float)((f - fl) * (f + fl));
+      }
+      for (int i = threadIdx.x; i < nop * FB; i += blockDim.x) {
+        const double fk = orow[(i / FB) * kOS + MWRT_O2_F], f = fblk[i % FB];
+        a32o[i] = (float)((f - fk) * (f + fk));
+      }
     }
     for (int i = threadIdx.x; i < nh; i += blockDim.x) {
       double fl = hrow[i * kHS + MWRT_H2O_FL];
@@ -412,7 +449,13 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
 
   const long long obase = (pidx * F + f0) * (long long)L + lev;  // + j*L per frequency
   const double2* fsq2 = reinterpret_cast<const double2*>(fsq);   // fsq is 16-byte aligned (even offsets)
+  // frequencies per staged group of the pair loop: a divisor-friendly size near MWRT_ABS_GROUP
+  constexpr int kGroupWish = MWRT_ABS_GROUP > 0 ? MWRT_ABS_GROUP : 1;
+  constexpr int kGroup = (FB % kGroupWish == 0) ? kGroupWish
+                         : (FB % 8 == 0 ? 8 : (FB % 5 == 0 ? 5 : (FB % 4 == 0 ? 4 : kGroupWish)));
   double acc[FB];
+  float accf[F32 ? FB : 1];   // fp32 mode: the pair-loop sums of one species (scaled by 2^40); the fp64
+                              // `acc` then only collects the corrections
   double tmp[FB];  // slow-path scratch (local memory, dynamically indexed)
 
   // ------------------------------------------------------------------ H2O (abh2o)
@@ -453,6 +496,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
       h.c4 = 4.0 * fc2 * h.wsq;
       h.n1 = 2.0 * (h.sp * h.w);
       h.n0 = h.n1 * (2.0 * fc2);
+      h.b32 = fma(h.shift, 2.0 * R[MWRT_H2O_FL] + h.shift, -h.wsq);
       return h;
     };
     // does the fast form of this line need a correction at some frequency of the block?
@@ -465,6 +509,10 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
 
 #pragma unroll
     for (int j = 0; j < FB; ++j) acc[j] = 0.0;
+    if constexpr (F32) {
+#pragma unroll
+      for (int j = 0; j < FB; ++j) accf[j] = 0.0f;
+    }
     double basesum = 0.0;
     const int n_in = cnt[0], n_act = cnt[1];
     const int npairs = (n_in + 1) >> 1;
@@ -494,16 +542,24 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
         const bool margin_ok = (fabs(ga.shift) < 1.0) && (fabs(gb.shift) < 1.0);
         if (margin_ok) {
           const double zb = has_b ? 1.0 : 0.0;   // odd count: the last pair's second line is a dummy
-          const PairHot h{ga.c3, ga.c4, ga.n1, ga.n0, gb.c3, gb.c4, gb.n1 * zb, gb.n0 * zb};
           basesum += 2.0 * ga.sp * ga.base + (2.0 * gb.sp * gb.base) * zb;
+          if constexpr (F32) {
+            const PairHotF h{(float)ga.b32, (float)ga.c4, (float)(ga.n1 * kF32Scale), (float)(ga.n0 * kF32Scale),
+                             (float)gb.b32, (float)gb.c4, (float)(gb.n1 * (zb * kF32Scale)),
+                             (float)(gb.n0 * (zb * kF32Scale))};
+            const float* Aa = a32h + ia * FB;
+            const float* Ab = a32h + ib * FB;
 #pragma unroll
-          for (int j = 0; j < FB; ++j) {
-            const double u = (j & 1) ? fsq2[j >> 1].y : fsq2[j >> 1].x;   // LDS.128: two frequencies per load
-            const double va = u - h.c3a, vb = u - h.c3b;
-            const double Da = fma(va, va, h.c4a), Db = fma(vb, vb, h.c4b);
-            const double na = fma(h.n1a, va, h.n0a), nb = fma(h.n1b, vb, h.n0b);
-            const double num = fma(nb, Da, na * Db);
-            acc[j] = fma(num, rcp_nr1(Da * Db), acc[j]);
+            for (int j = 0; j < FB; ++j) {
+              const float va = Aa[j] - h.ba, vb = Ab[j] - h.bb;
+              const float Da = fmaf(va, va, h.c4a), Db = fmaf(vb, vb, h.c4b);
+              const float na = fmaf(h.n1a, va, h.n0a), nb = fmaf(h.n1b, vb, h.n0b);
+              const float num = fmaf(nb, Da, na * Db);
+              accf[j] = fmaf(num, rcp_f32(Da * Db), accf[j]);
+            }
+          } else {
+          const PairHot h{ga.c3, ga.c4, ga.n1, ga.n0, gb.c3, gb.c4, gb.n1 * zb, gb.n0 * zb};
+          pair_accumulate<FB, kGroup>(acc, fsq2, h);
           }
           if (hchk[ia] | hchk[ib]) {   // uniform: almost every pair skips the per-thread tests
             ma = (hchk[ia] && needs_corr(ga, ia, Ra[MWRT_H2O_FL])) ? kSlowCorr : kSlowNone;
@@ -627,7 +683,8 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
 #pragma unroll
     for (int j = 0; j < FB; ++j) {
       const double f = fblk[j];
-      double a = (f * f) * fma(lc, acc[j] - basesum, conbase);
+      const double lsum = F32 ? fma((double)accf[j], kF32Unscale, acc[j]) : acc[j];
+      double a = (f * f) * fma(lc, lsum - basesum, conbase);
       if (rho <= 0.0) a = 0.0;
       if (in_bad) a = nan("");
       if (f0 + j < F) awet[obase + (long long)j * L] = a;
@@ -668,11 +725,17 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
       o.c4 = 4.0 * fc2 * o.df2;
       o.n1 = 2.0 * (as + pp_);
       o.n0 = 4.0 * fma(as, fc2, -pp_ * o.df2);
+      const double dnu = o.fcen - R[MWRT_O2_F];
+      o.b32 = fma(dnu, 2.0 * R[MWRT_O2_F] + dnu, -o.df2);
       return o;
     };
 
 #pragma unroll
     for (int j = 0; j < FB; ++j) acc[j] = 0.0;
+    if constexpr (F32) {
+#pragma unroll
+      for (int j = 0; j < FB; ++j) accf[j] = 0.0f;
+    }
     // The line strengths need one exp each.  They are evaluated G at a time, interleaved
     // (exp_tb_vec), so the FP64 pipe sees G independent chains; the values are handed to the pair
     // loop by rotating a small register array (no dynamic indexing).
@@ -693,15 +756,22 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
         for (int q = 0; q + 2 < G; ++q) ev[q] = ev[q + 2];
         const O2Line oa = hoist(k, expa);
         const O2Line ob = hoist(k + 1, expb);
-        const PairHot h{oa.c3, oa.c4, oa.n1, oa.n0, ob.c3, ob.c4, ob.n1, ob.n0};
+        if constexpr (F32) {
+          const PairHotF h{(float)oa.b32, (float)oa.c4, (float)(oa.n1 * kF32Scale), (float)(oa.n0 * kF32Scale),
+                           (float)ob.b32, (float)ob.c4, (float)(ob.n1 * kF32Scale), (float)(ob.n0 * kF32Scale)};
+          const float* Aa = a32o + k * FB;
+          const float* Ab = a32o + (k + 1) * FB;
 #pragma unroll
-        for (int j = 0; j < FB; ++j) {
-          const double u = (j & 1) ? fsq2[j >> 1].y : fsq2[j >> 1].x;   // LDS.128: two frequencies per load
-          const double va = u - h.c3a, vb = u - h.c3b;
-          const double Da = fma(va, va, h.c4a), Db = fma(vb, vb, h.c4b);
-          const double na = fma(h.n1a, va, h.n0a), nb = fma(h.n1b, vb, h.n0b);
-          const double num = fma(nb, Da, na * Db);
-          acc[j] = fma(num, rcp_nr1(Da * Db), acc[j]);
+          for (int j = 0; j < FB; ++j) {
+            const float va = Aa[j] - h.ba, vb = Ab[j] - h.bb;
+            const float Da = fmaf(va, va, h.c4a), Db = fmaf(vb, vb, h.c4b);
+            const float na = fmaf(h.n1a, va, h.n0a), nb = fmaf(h.n1b, vb, h.n0b);
+            const float num = fmaf(nb, Da, na * Db);
+            accf[j] = fmaf(num, rcp_f32(Da * Db), accf[j]);
+          }
+        } else {
+        const PairHot h{oa.c3, oa.c4, oa.n1, oa.n0, ob.c3, ob.c4, ob.n1, ob.n0};
+        pair_accumulate<FB, kGroup>(acc, fsq2, h);
         }
         // rare: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency
         if (!(ochk[k] | ochk[k + 1])) continue;   // uniform, decided per CTA
@@ -745,7 +815,8 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
       const double f = fblk[j];
       const double f2 = f * f;
       const double nonres = m.o2_nonres * dfnr * rcp_fast(th * fma(dfnr, dfnr, f2));
-      double o2 = scale * (f2 * (nonres + acc[j]));
+      const double lsum = F32 ? fma((double)accf[j], kF32Unscale, acc[j]) : acc[j];
+      double o2 = scale * (f2 * (nonres + lsum));
       o2 = (o2 < 0.0) ? 0.0 : o2;  // max(o2abs, 0)
       o2 *= m.o2_iso;
       double fdep = 1.0;
@@ -759,41 +830,14 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
     }
   }
 
-  // ------------------------------------------------------------------ cloud
-  if (aliq) {
-    const double denl = denliq ? denliq[ipt] : 0.0;
-    const bool wet = denl > 0.0 || isnan(denl);
-    LiqPrep lq;
-    if (wet) lq = liq_prepare(m.liq_model, tk);   // temperature-only terms, once per level-point
-#pragma unroll 1
-    for (int j = 0; j < FB; ++j) {
-      double a = 0.0;
-      if (wet) a = liq_abs_eval(m.liq_model, lq, fblk[j]) * denl;
-      if (in_bad) a = nan("");
-      if (f0 + j < F) aliq[obase + (long long)j * L] = a;
-    }
-  }
-  if (aice) {
-    const double deni = denice ? denice[ipt] : 0.0;
-#pragma unroll 1
-    for (int j = 0; j < FB; ++j) {
-      const double f = fblk[j];
-      const double wave = kLightC / (f * 1e9);
-      double a = 0.0;
-      if (deni > 0.0 || isnan(deni)) a = ((8.18645 / wave) * deni * 0.000959553) * kDb2Np;
-      if (in_bad) a = nan("");
-      if (f0 + j < F) aice[obase + (long long)j * L] = a;
-    }
-  }
   }   // in_range
   }   // work items
 }
 
-template <int FB>
+template <int FB, bool F32>
 static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, const double* tk,
-                      const double* e, int e_is_rh, double* e_out, double* rho_out,
-                      const double* denliq, const double* denice, const double* frq, double* awet,
-                      double* adry, double* aliq, double* aice, int* status, cudaStream_t st) {
+                      const double* e, int e_is_rh, double* e_out, double* rho_out, const double* frq,
+                      double* awet, double* adry, int* status, cudaStream_t st) {
   const long long npts = (long long)P * L;
   const int nfb = (F + FB - 1) / FB;
   const long long items = ((npts + kAbsThreads - 1) / kAbsThreads) * nfb;
@@ -803,33 +847,92 @@ static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, c
   // and lets the warps of a CTA drift apart (more instruction-cache misses).  The item loop in the
   // kernel only matters beyond 2^31-1 items.
   const unsigned grid = (unsigned)(items < 0x7fffffffLL ? items : 0x7fffffffLL);
-  size_t smem = sizeof(double) * (size_t)abs_smem_doubles(m.n_h2o, m.n_o2, FB);
-  k_absorption<FB><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, nfb, p, tk, e, e_is_rh, e_out, rho_out,
-                                                    denliq, denice, frq, awet, adry, aliq, aice,
-                                                    status);
+  const int nop = (m.n_o2 + 1) & ~1;
+  size_t smem = sizeof(double) * (size_t)abs_smem_doubles(m.n_h2o, m.n_o2, FB) +
+                (F32 ? sizeof(float) * (size_t)(m.n_h2o + nop) * FB : 0);
+  if (smem > 48 * 1024) {
+    static bool once = [] {
+      return cudaFuncSetAttribute(k_absorption<FB, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  96 * 1024) == cudaSuccess;
+    }();
+    if (!once) return fail_arg(MWRT_E_STATE, "k_absorption: cannot raise the dynamic shared-memory limit");
+  }
+  k_absorption<FB, F32><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, nfb, p, tk, e, e_is_rh, e_out,
+                                                         rho_out, frq, awet, adry, status);
   MWRT_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-// frequency-block choice: exact fit for the 14 HATPRO channels (and 14*k sub-band sets), else 16/8
+// frequency-block choice: exact fit for the 14 HATPRO channels (and 14*k sub-band sets), else 16/8;
+// long lists take wide blocks.  f32ls selects the fp32 line-shape instantiation.
 int absorption_launch(const ModelDev& m, int P, int L, int F, const double* p, const double* tk,
-                      const double* e, int e_is_rh, double* e_out, double* rho_out,
-                      const double* denliq, const double* denice, const double* frq, double* awet,
-                      double* adry, double* aliq, double* aice, int* status, cudaStream_t st) {
-#define MWRT_ABS_ARGS m, P, L, F, p, tk, e, e_is_rh, e_out, rho_out, denliq, denice, frq, awet, adry, aliq, aice, status, st
-  // wide blocks for long frequency lists: the hoisted line parameters (40 % of a 14-wide block's FP64
-  // work) are then shared by twice as many frequencies, at 3 instead of 4 CTAs per SM
-  static const int wide = [] { const char* e = getenv("MWRT_ABS_WIDE"); return e ? atoi(e) : 1; }();
+                      const double* e, int e_is_rh, double* e_out, double* rho_out, const double* frq,
+                      double* awet, double* adry, int* status, int f32ls, cudaStream_t st) {
+#define MWRT_ABS_ARGS m, P, L, F, p, tk, e, e_is_rh, e_out, rho_out, frq, awet, adry, status, st
+#define MWRT_ABS_GO(FB_) return f32ls ? launch_abs<FB_, true>(MWRT_ABS_ARGS) : launch_abs<FB_, false>(MWRT_ABS_ARGS)
+  // Block width for long frequency lists (MWRT_ABS_WIDE=0 switches the 28/32-wide blocks off): the
+  // hoisted line parameters (40 % of a 14-wide block's FP64 work) are shared by every frequency of the
+  // block.  Measured on B200 (profiles/r02b_*): 50-70-wide blocks at 2 CTAs per SM (255 registers) are
+  // SLOWER than 28/32 at 3 CTAs per SM -- config 3 share 84.8 ms against 74.6 ms, config 4 +9 % -- the
+  // lost occupancy costs more than the hoist saves; they were dropped.
+  const char* wenv = getenv("MWRT_ABS_WIDE");   // read per call: tests and tuning runs switch it
+  const int wide = wenv ? atoi(wenv) : MWRT_ABS_WIDE_DEFAULT;
   if (wide && F >= 112) {
-    if (F % 32 == 0) return launch_abs<32>(MWRT_ABS_ARGS);
-    if (F % 28 == 0) return launch_abs<28>(MWRT_ABS_ARGS);
-    if (F % 16 != 0 && F % 14 != 0) return launch_abs<32>(MWRT_ABS_ARGS);
+    if (F % 32 == 0) MWRT_ABS_GO(32);
+    if (F % 28 == 0) MWRT_ABS_GO(28);
+    if (F % 16 != 0 && F % 14 != 0) MWRT_ABS_GO(32);
   }
-  if (F % 16 == 0) return launch_abs<16>(MWRT_ABS_ARGS);
-  if (F % 14 == 0) return launch_abs<14>(MWRT_ABS_ARGS);
-  if (F <= 8) return launch_abs<8>(MWRT_ABS_ARGS);
-  return launch_abs<16>(MWRT_ABS_ARGS);
+  if (F % 16 == 0) MWRT_ABS_GO(16);
+  if (F % 14 == 0) MWRT_ABS_GO(14);
+  if (F <= 8) MWRT_ABS_GO(8);
+  MWRT_ABS_GO(16);
+#undef MWRT_ABS_GO
 #undef MWRT_ABS_ARGS
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stage entry point only: cloud liquid / ice absorption (P,F,L) elementwise, level fastest.  The fused
+// path never materialises these arrays (kernel 3 evaluates mwrt_cloud.cuh inline).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_cloud_abs(const int liq_model, const long long n, const int L, const int F,
+                            const double* __restrict__ tk, const double* __restrict__ denliq,
+                            const double* __restrict__ denice, const double* __restrict__ frq,
+                            double* __restrict__ aliq, double* __restrict__ aice) {
+  __shared__ double etab[kExpTabN];
+  __shared__ __align__(16) double ltab[128];
+  exp_tab_stage(etab);
+  log_tab_stage(ltab);
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (p, f, l)
+  if (i >= n) return;
+  const int lev = (int)(i % L);
+  const long long pf = i / L;
+  const int jf = (int)(pf % F);
+  const long long ipt = (pf / F) * L + lev;
+  const double t = tk[ipt], f = frq[jf];
+  const bool t_bad = isnan(t) || !(t > 50.0 && t < 1000.0);   // same window as kernel 1
+  if (aliq) {
+    const double denl = denliq ? denliq[ipt] : 0.0;
+    double a = 0.0;
+    if (denl > 0.0 || isnan(denl)) a = liq_abs_unit(liq_model, t, f, etab, ltab) * denl;
+    aliq[i] = t_bad ? nan("") : a;
+  }
+  if (aice) {
+    const double deni = denice ? denice[ipt] : 0.0;
+    double a = 0.0;
+    if (deni > 0.0 || isnan(deni)) a = ice_abs(f, deni);
+    aice[i] = t_bad ? nan("") : a;
+  }
+}
+
+int cloud_abs_launch(const ModelDev& m, int P, int L, int F, const double* tk, const double* denliq,
+                     const double* denice, const double* frq, double* aliq, double* aice,
+                     cudaStream_t st) {
+  const long long n = (long long)P * F * L;
+  k_cloud_abs<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m.liq_model, n, L, F, tk, denliq, denice, frq,
+                                                          aliq, aice);
+  MWRT_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 // RTEquation.vapor as a standalone stage

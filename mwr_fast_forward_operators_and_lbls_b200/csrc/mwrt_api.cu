@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "mwrt_common.cuh"
+#include "mwrt_rte_args.h"
+#include <nvtx3/nvToolsExt.h>
 #include <stdio.h>
 #include <time.h>
 #include <stdlib.h>
@@ -30,15 +32,13 @@ int fail_arg(int code, const char* what) {
 
 // launchers defined in mwrt_absorption.cu / mwrt_rte.cu
 int absorption_launch(const ModelDev& m, int P, int L, int F, const double* p, const double* tk,
-                      const double* e, int e_is_rh, double* e_out, double* rho_out,
-                      const double* denliq, const double* denice, const double* frq, double* awet,
-                      double* adry, double* aliq, double* aice, int* status, cudaStream_t st);
+                      const double* e, int e_is_rh, double* e_out, double* rho_out, const double* frq,
+                      double* awet, double* adry, int* status, int f32ls, cudaStream_t st);
+int cloud_abs_launch(const ModelDev& m, int P, int L, int F, const double* tk, const double* denliq,
+                     const double* denice, const double* frq, double* aliq, double* aice, cudaStream_t st);
 int vapor_launch(long long n, const double* tk, const double* rh, double* e, double* rho, cudaStream_t st);
-int rte_launch(int P, int L, int F, int A, const double* tk, const double* awet, const double* adry,
-               const double* aliq, const double* aice, const double* ds, const double* z,
-               const double* amass, const double* frq, int from_sat, double emis, double* tbtotal,
-               double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
-               double* tauice, double* tau_layer, int tl_angle, int* status, const Fanout& fo, cudaStream_t st);
+int rte_launch(const RteArgs& g, int from_sat, const Fanout& fo, cudaStream_t st);
+int tmrcld_launch(const RteArgs& g, const int* ibase, const int* itop, double* out, cudaStream_t st);
 int slant_path_launch(int P, int L, int A, const double* z, const double* p, const double* tk,
                       const double* e, const double* angles, int ray_tracing, double* ds, int* status,
                       cudaStream_t st);
@@ -80,40 +80,48 @@ struct mwrt_model {
 constexpr int kSlots = 4;   // workspace slots = compute streams of the host pipeline
 
 struct mwrt_plan {
-  ModelDev model;
-  int L, F, A, flags, chunk;
-  double emis;
-  int C, S;          // band-pass (C == 0: off)
-  double* d_frq;
-  double* d_angles;
-  double* d_amass;   // (A,) 1/sin(elevation), computed on the host like PyRTlib does
-  double* d_bpw;     // (C,S) weights or null (uniform)
+  // every member carries a default initialiser: `new mwrt_plan()` yields a plan that
+  // mwrt_plan_destroy can always take apart, however far mwrt_plan_create got
+  ModelDev model{};
+  int L = 0, F = 0, A = 0, flags = 0, chunk = 0;
+  double emis = 1.0;
+  int C = 0, S = 0;            // band-pass (C == 0: off)
+  int bp_cpb = 0;              // > 0: the band-pass is reduced inside kernel 3, this many channels per CTA
+  int f32ls = 0;               // fp32 line-shape mode of kernel 1 (mwrt_plan_set_precision)
+  double* d_frq = nullptr;
+  double* d_angles = nullptr;
+  double* d_amass = nullptr;   // (A,) 1/sin(elevation), computed on the host like PyRTlib does
+  double* d_bpw = nullptr;     // (C,S) weights or null (uniform)
   // workspace for `cap` profiles, in `nslots` (1 or 2) independent slots: with two slots kernel 3 of
   // chunk c runs on `s_aux` while kernel 1 of chunk c+1 runs on the caller's stream
-  int cap, nslots, split;
-  Fanout fanout;     // how kernel 3 (or the band-pass epilogue) stores the (P,F,A) results
+  int cap = 0, nslots = 0, split = 1;
+  Fanout fanout{MWRT_OUT_PLAIN, 0, {0}};   // how kernel 3 stores the (P,F,A) results
   struct Slot {
-    double *awet, *adry, *aliq, *aice, *ds, *e;
-    double* mono[7];  // monochromatic RTE outputs when band-pass is on
-    cudaEvent_t ev_abs, ev_rte;
-    bool used;
+    double *awet = nullptr, *adry = nullptr, *aliq = nullptr, *aice = nullptr, *ds = nullptr, *e = nullptr;
+    // monochromatic RTE outputs, only for the UNFUSED band-pass fallback (sub-bands wider than one CTA,
+    // ray tracing, or fan-out stores); the normal band-pass is reduced inside kernel 3
+    double* mono[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_abs = nullptr, ev_rte = nullptr;
+    bool used = false;
   } ws[kSlots];
-  cudaStream_t s_aux;
+  cudaStream_t s_aux = nullptr;
   // host-path resources (lazily created)
   // Device staging holds the WHOLE batch (inputs, outputs, status: 100 MB for 10^4 profiles), so
   // neither copy engine ever waits for a buffer to be recycled; only the (P,F,L) tau_layer field,
   // which can be tens of GB, is staged per chunk in two slots.
-  bool host_ready;
-  cudaStream_t s_h2d, s_comp, s_d2h;
-  cudaStream_t s_cmp[kSlots];                 // s_cmp[0] = s_comp, s_cmp[1] = s_aux, others own
+  bool host_ready = false;
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaStream_t s_cmp[kSlots] = {nullptr, nullptr, nullptr, nullptr};   // s_cmp[0] = s_comp, s_cmp[1] = s_aux, others own
   std::vector<cudaEvent_t> ev_h2d, ev_comp;   // one per chunk
-  cudaEvent_t ev_tl[2];                       // tau_layer slot copied back
-  int hcap, hcap_tl;
-  double* h_in;       // 6 x hcap x L, field-major
-  double* h_out;      // 7 x hcap x Fo x A, field-major
-  double* h_tl[2];
-  int* h_status;
+  cudaEvent_t ev_tl[2] = {nullptr, nullptr};  // tau_layer slot copied back
+  int hcap = 0, hcap_tl = 0;
+  size_t mem_pitch = 0;        // cudaDeviceProp::memPitch: upper bound of a 2-D copy's pitches
+  double* h_in = nullptr;      // 6 x hcap x L, field-major
+  double* h_out = nullptr;     // 7 x hcap x Fo x A, field-major
+  double* h_tl[2] = {nullptr, nullptr};
+  int* h_status = nullptr;
 };
+static_assert(kSlots == 4, "s_cmp initialiser lists four streams");
 
 extern "C" {
 
@@ -231,14 +239,32 @@ int mwrt_vapor_f64(int64_t n, const double* tk, const double* rh, double* e, dou
   return vapor_launch(n, tk, rh, e, rho, (cudaStream_t)stream);
 }
 
+static int absorption_stage(const mwrt_model* m, int P, int L, int F, const double* p, const double* tk,
+                            const double* e, const double* denliq, const double* denice, const double* frq,
+                            double* awet, double* adry, double* aliq, double* aice, int32_t* status,
+                            int f32ls, void* stream) {
+  if (!m || P <= 0 || L <= 0 || F <= 0 || !p || !tk || !e || !frq || !awet || !adry)
+    return fail_arg(MWRT_E_ARG, "mwrt_absorption: bad argument");
+  int rc = absorption_launch(m->dev, P, L, F, p, tk, e, 0, nullptr, nullptr, frq, awet, adry, status, f32ls,
+                             (cudaStream_t)stream);
+  if (rc) return rc;
+  if (aliq || aice)   // RTEquation.cloudy_absorption, elementwise (the fused path evaluates it inside kernel 3)
+    rc = cloud_abs_launch(m->dev, P, L, F, tk, denliq, denice, frq, aliq, aice, (cudaStream_t)stream);
+  return rc;
+}
+
 int mwrt_absorption_f64(const mwrt_model* m, int P, int L, int F, const double* p, const double* tk,
                         const double* e, const double* denliq, const double* denice, const double* frq,
                         double* awet, double* adry, double* aliq, double* aice, int32_t* status,
                         void* stream) {
-  if (!m || P <= 0 || L <= 0 || F <= 0 || !p || !tk || !e || !frq || !awet || !adry)
-    return fail_arg(MWRT_E_ARG, "mwrt_absorption_f64: bad argument");
-  return absorption_launch(m->dev, P, L, F, p, tk, e, 0, nullptr, nullptr, denliq, denice, frq, awet,
-                           adry, aliq, aice, status, (cudaStream_t)stream);
+  return absorption_stage(m, P, L, F, p, tk, e, denliq, denice, frq, awet, adry, aliq, aice, status, 0, stream);
+}
+
+int mwrt_absorption_f32ls(const mwrt_model* m, int P, int L, int F, const double* p, const double* tk,
+                          const double* e, const double* denliq, const double* denice, const double* frq,
+                          double* awet, double* adry, double* aliq, double* aice, int32_t* status,
+                          void* stream) {
+  return absorption_stage(m, P, L, F, p, tk, e, denliq, denice, frq, awet, adry, aliq, aice, status, 1, stream);
 }
 
 int mwrt_slant_path_f64(int P, int L, int A, const double* z, const double* p, const double* tk,
@@ -262,9 +288,14 @@ int mwrt_rte_f64(int P, int L, int F, int A, const double* tk, const double* awe
     return fail_arg(MWRT_E_ARG, "mwrt_rte_f64: aliq and aice must be given together");
   if (tau_layer && (tau_layer_angle < 0 || tau_layer_angle >= A))
     return fail_arg(MWRT_E_ARG, "mwrt_rte_f64: tau_layer_angle out of range");
-  return rte_launch(P, L, F, A, tk, awet, adry, aliq, aice, ds, nullptr, nullptr, frq, from_sat, emissivity, tbtotal,
-                    tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tau_layer_angle, status,
-                    Fanout{MWRT_OUT_PLAIN, 0, {0}}, (cudaStream_t)stream);
+  RteArgs g{};
+  g.P = P; g.L = L; g.F = F; g.A = A;
+  g.tk = tk; g.awet = awet; g.adry = adry; g.aliq = aliq; g.aice = aice;
+  g.ds = ds; g.frq = frq; g.emis = emissivity;
+  g.tbtotal = tbtotal; g.tbatm = tbatm; g.tmr = tmr; g.tauwet = tauwet; g.taudry = taudry;
+  g.tauliq = tauliq; g.tauice = tauice; g.tau_layer = tau_layer; g.tl_angle = tau_layer_angle;
+  g.status = status;
+  return rte_launch(g, from_sat, Fanout{MWRT_OUT_PLAIN, 0, {0}}, (cudaStream_t)stream);
 }
 
 int mwrt_bandpass_f64(int P, int C, int S, int A, const double* in, const double* w, double* out,
@@ -275,12 +306,17 @@ int mwrt_bandpass_f64(int P, int C, int S, int A, const double* in, const double
 }
 
 // ------------------------------------------------------------------------------------ plan
+// is the band-pass of this plan reduced inside kernel 3?  (else: monochromatic fields + k_bandpass)
+static bool bp_fused(const mwrt_plan* pl) {
+  return pl->C > 0 && pl->bp_cpb > 0 && !(pl->flags & MWRT_F_RAY_TRACING) && pl->fanout.mode == MWRT_OUT_PLAIN;
+}
+
 static void plan_free_ws(mwrt_plan* pl) {
   for (int k = 0; k < kSlots; ++k) {
     mwrt_plan::Slot& w = pl->ws[k];
-    cudaFree(w.awet); cudaFree(w.adry); cudaFree(w.aliq); cudaFree(w.aice); cudaFree(w.ds); cudaFree(w.e);
+    cudaFree(w.awet); cudaFree(w.adry); cudaFree(w.ds); cudaFree(w.e);
     for (int i = 0; i < 7; ++i) cudaFree(w.mono[i]);
-    w.awet = w.adry = w.aliq = w.aice = w.ds = w.e = nullptr;
+    w.awet = w.adry = w.ds = w.e = nullptr;
     for (int i = 0; i < 7; ++i) w.mono[i] = nullptr;
     w.used = false;
   }
@@ -288,8 +324,13 @@ static void plan_free_ws(mwrt_plan* pl) {
   pl->nslots = 0;
 }
 
+// Workspace of one slot: awet, adry (cap,F,L) -- cloud liquid/ice absorption is evaluated inside
+// kernel 3 and has no array --, e (cap,L), ds (cap,A,L) for ray tracing; the monochromatic result
+// fields only for the unfused band-pass fallback.
 static int plan_reserve(mwrt_plan* pl, int cap, int nslots) {
-  if (cap <= pl->cap && nslots <= pl->nslots) return 0;
+  const bool need_mono = pl->C > 0 && !bp_fused(pl);
+  const bool have_mono = pl->nslots > 0 && pl->ws[0].mono[0] != nullptr;
+  if (cap <= pl->cap && nslots <= pl->nslots && (!need_mono || have_mono)) return 0;
   cap = std::max(cap, pl->cap);
   nslots = std::max(nslots, pl->nslots);
   plan_free_ws(pl);
@@ -298,14 +339,10 @@ static int plan_reserve(mwrt_plan* pl, int cap, int nslots) {
     mwrt_plan::Slot& w = pl->ws[k];
     MWRT_CUDA_OK(cudaMalloc(&w.awet, pfl));
     MWRT_CUDA_OK(cudaMalloc(&w.adry, pfl));
-    if (pl->flags & MWRT_F_CLOUDY) {
-      MWRT_CUDA_OK(cudaMalloc(&w.aliq, pfl));
-      MWRT_CUDA_OK(cudaMalloc(&w.aice, pfl));
-    }
     if (pl->flags & MWRT_F_RAY_TRACING)
       MWRT_CUDA_OK(cudaMalloc(&w.ds, sizeof(double) * (size_t)cap * pl->A * pl->L));
     MWRT_CUDA_OK(cudaMalloc(&w.e, sizeof(double) * (size_t)cap * pl->L));
-    if (pl->C > 0)
+    if (need_mono)
       for (int i = 0; i < 7; ++i)
         MWRT_CUDA_OK(cudaMalloc(&w.mono[i], sizeof(double) * (size_t)cap * pl->F * pl->A));
   }
@@ -314,10 +351,10 @@ static int plan_reserve(mwrt_plan* pl, int cap, int nslots) {
   return 0;
 }
 
-static int default_chunk(int L, int F, int flags) {
-  // bound the (chunk,F,L) absorption workspace to ~1 GiB; it is streamed once (write, then read) and
-  // costs < 5 % of the FP64 time even when it spills out of the 126 MB L2
-  const double per_profile = 8.0 * F * L * ((flags & MWRT_F_CLOUDY) ? 4 : 2);
+static int default_chunk(int L, int F) {
+  // bound the two (chunk,F,L) absorption arrays to ~1 GiB; they are streamed once (write, then read)
+  // and cost < 5 % of the FP64 time even when they spill out of the 126 MB L2
+  const double per_profile = 8.0 * F * L * 2;
   double c = (1024.0 * 1024.0 * 1024.0) / per_profile;
   if (c < 64) c = 64;
   if (c > (1 << 20)) c = (1 << 20);
@@ -328,13 +365,10 @@ int mwrt_plan_create(const mwrt_model* m, int L, int F, int A, const double* frq
                      int flags, int chunk_profiles, mwrt_plan** out) {
   if (!m || !frq || !angles || !out || L < 2 || F < 1 || A < 1)
     return fail_arg(MWRT_E_ARG, "mwrt_plan_create: bad argument");
-  mwrt_plan* pl = new mwrt_plan();
-  memset(pl, 0, sizeof(*pl));
+  mwrt_plan* pl = new mwrt_plan();   // value-initialised: see the member initialisers
   pl->model = m->dev;
   pl->L = L; pl->F = F; pl->A = A; pl->flags = flags;
-  pl->chunk = chunk_profiles > 0 ? chunk_profiles : default_chunk(L, F, flags);
-  pl->emis = 1.0;
-  pl->split = 1;
+  pl->chunk = chunk_profiles > 0 ? chunk_profiles : default_chunk(L, F);
   cudaError_t e = cudaStreamCreateWithFlags(&pl->s_aux, cudaStreamNonBlocking);
   for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
     e = cudaEventCreateWithFlags(&pl->ws[k].ev_abs, cudaEventDisableTiming);
@@ -348,9 +382,15 @@ int mwrt_plan_create(const mwrt_model* m, int L, int F, int A, const double* frq
   for (int a = 0; a < A; ++a) amass[a] = 1.0 / sin(angles[a] * 3.141592653589793 / 180.0);
   if (e == cudaSuccess) e = cudaMalloc(&pl->d_amass, sizeof(double) * A);
   if (e == cudaSuccess) e = cudaMemcpy(pl->d_amass, amass.data(), sizeof(double) * A, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    int dev = 0;
+    cudaDeviceProp prop;
+    e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+    if (e == cudaSuccess) pl->mem_pitch = prop.memPitch;
+  }
   if (e != cudaSuccess) {
-    cudaFree(pl->d_frq); cudaFree(pl->d_angles); cudaFree(pl->d_amass);
-    delete pl;
+    mwrt_plan_destroy(pl);   // releases whatever exists: stream, events, device arrays
     return fail_cuda(e, "mwrt_plan_create");
   }
   *out = pl;
@@ -365,14 +405,20 @@ static void plan_free_host(mwrt_plan* pl) {
   for (int s = 0; s < 2; ++s) {
     cudaFree(pl->h_tl[s]);
     pl->h_tl[s] = nullptr;
-    cudaEventDestroy(pl->ev_tl[s]);
+    if (pl->ev_tl[s]) cudaEventDestroy(pl->ev_tl[s]);
+    pl->ev_tl[s] = nullptr;
   }
   for (cudaEvent_t e : pl->ev_h2d) cudaEventDestroy(e);
   for (cudaEvent_t e : pl->ev_comp) cudaEventDestroy(e);
   pl->ev_h2d.clear();
   pl->ev_comp.clear();
-  cudaStreamDestroy(pl->s_h2d); cudaStreamDestroy(pl->s_comp); cudaStreamDestroy(pl->s_d2h);
-  for (int k = 2; k < kSlots; ++k) cudaStreamDestroy(pl->s_cmp[k]);
+  if (pl->s_h2d) cudaStreamDestroy(pl->s_h2d);
+  if (pl->s_comp) cudaStreamDestroy(pl->s_comp);
+  if (pl->s_d2h) cudaStreamDestroy(pl->s_d2h);
+  for (int k = 2; k < kSlots; ++k)
+    if (pl->s_cmp[k]) cudaStreamDestroy(pl->s_cmp[k]);
+  pl->s_h2d = pl->s_comp = pl->s_d2h = nullptr;
+  for (int k = 0; k < kSlots; ++k) pl->s_cmp[k] = nullptr;
   pl->h_in = pl->h_out = nullptr;
   pl->h_status = nullptr;
   pl->host_ready = false;
@@ -399,6 +445,13 @@ int mwrt_plan_set_emissivity(mwrt_plan* pl, double es) {
   return 0;
 }
 
+int mwrt_plan_set_precision(mwrt_plan* pl, int precision) {
+  if (!pl || (precision != MWRT_PREC_F64 && precision != MWRT_PREC_F32_LINESHAPE))
+    return fail_arg(MWRT_E_ARG, "mwrt_plan_set_precision: bad argument");
+  pl->f32ls = precision == MWRT_PREC_F32_LINESHAPE;
+  return 0;
+}
+
 int mwrt_plan_set_output_fanout(mwrt_plan* pl, int mode, int npeer, const int64_t* peer_byte_offsets) {
   if (!pl || mode < MWRT_OUT_PLAIN || mode > MWRT_OUT_PEERS)
     return fail_arg(MWRT_E_ARG, "mwrt_plan_set_output_fanout: bad argument");
@@ -410,6 +463,12 @@ int mwrt_plan_set_output_fanout(mwrt_plan* pl, int mode, int npeer, const int64_
     for (int r = 0; r < npeer; ++r) f.off[r] = (long long)peer_byte_offsets[r];
   }
   pl->fanout = f;
+  return 0;
+}
+
+int mwrt_push_async(void* dst, const void* src, int64_t bytes, void* stream) {
+  if (!dst || !src || bytes <= 0) return fail_arg(MWRT_E_ARG, "mwrt_push_async: bad argument");
+  MWRT_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
 }
 
@@ -432,6 +491,7 @@ int mwrt_plan_set_bandpass(mwrt_plan* pl, int C, int S, const double* weights) {
     MWRT_CUDA_OK(cudaMemcpy(pl->d_bpw, weights, sizeof(double) * C * S, cudaMemcpyHostToDevice));
   }
   pl->C = C; pl->S = S;
+  pl->bp_cpb = rte_bp_channels_per_cta(C, S);   // 0: a sub-band does not fit one CTA -> unfused fallback
   return 0;
 }
 
@@ -440,12 +500,13 @@ int mwrt_plan_launch_count(const mwrt_plan* pl, int P) {
   int chunk = std::min(P, pl->chunk);
   if (pl->split > 1 && P >= 1024 * pl->split) chunk = std::min(chunk, (P + pl->split - 1) / pl->split);
   const int nchunk = (P + chunk - 1) / chunk;
-  return nchunk * (2 + ((pl->flags & MWRT_F_RAY_TRACING) ? 1 : 0) + (pl->C > 0 ? 7 : 0));
+  const int bp = (pl->C > 0 && !bp_fused(pl)) ? 7 : 0;   // unfused fallback: one k_bandpass per field
+  return nchunk * (2 + ((pl->flags & MWRT_F_RAY_TRACING) ? 1 : 0) + bp);
 }
 
 // one chunk: device pointers already offset to the chunk's first profile.  Kernel 1 (+2) go to
-// st_abs, kernel 3 (+ band-pass) to st_rte; when the two differ the hand-off and the reuse of the
-// workspace slot are ordered with the slot's events.
+// st_abs, kernel 3 to st_rte; when the two differ the hand-off and the reuse of the workspace slot
+// are ordered with the slot's events.
 static int forward_chunk(mwrt_plan* pl, int slot, int P, const mwrt_profiles& in,
                          const mwrt_outputs& out, cudaStream_t st_abs, cudaStream_t st_rte) {
   const bool cloudy = pl->flags & MWRT_F_CLOUDY;
@@ -455,39 +516,58 @@ static int forward_chunk(mwrt_plan* pl, int slot, int P, const mwrt_profiles& in
   mwrt_plan::Slot& w = pl->ws[slot];
   if (two && w.used) MWRT_CUDA_OK(cudaStreamWaitEvent(st_abs, w.ev_rte, 0));  // slot still being read?
   if (out.status) MWRT_CUDA_OK(cudaMemsetAsync(out.status, 0, sizeof(int) * (size_t)P, st_abs));
-  // kernel 1: vapour pressure + absorption (e is kept for the refractivity of kernel 2)
-  int rc = absorption_launch(pl->model, P, L, F, in.p, in.tk, in.rh, /*e_is_rh=*/1, w.e, nullptr,
-                             cloudy ? in.denliq : nullptr, cloudy ? in.denice : nullptr, pl->d_frq,
-                             w.awet, w.adry, cloudy ? w.aliq : nullptr, cloudy ? w.aice : nullptr,
-                             out.status, st_abs);
+  // kernel 1: vapour pressure + gas absorption (e is kept for the refractivity of kernel 2)
+  nvtxRangePushA("mwrt:absorption");
+  int rc = absorption_launch(pl->model, P, L, F, in.p, in.tk, in.rh, /*e_is_rh=*/1, w.e, nullptr, pl->d_frq,
+                             w.awet, w.adry, out.status, pl->f32ls, st_abs);
+  nvtxRangePop();
   if (rc) return rc;
   // kernel 2: refractive slant path (the plane-parallel default needs no kernel: kernel 3 forms
   // ds = dz / sin(elev) in registers)
   if (rt) {
+    nvtxRangePushA("mwrt:slant_path");
     rc = slant_path_launch(P, L, A, in.z, in.p, in.tk, w.e, pl->d_angles, 1, w.ds, out.status, st_abs);
+    nvtxRangePop();
     if (rc) return rc;
   }
   if (two) {
     MWRT_CUDA_OK(cudaEventRecord(w.ev_abs, st_abs));
     MWRT_CUDA_OK(cudaStreamWaitEvent(st_rte, w.ev_abs, 0));
   }
-  // kernel 3: RTE (+ band-pass epilogue)
+  // kernel 3: layer integration + RTE, cloud absorption inline, band-pass reduced in the kernel
+  const bool fused = bp_fused(pl);
   double* tl = (pl->flags & MWRT_F_TAU_LAYERS) ? out.tau_layer : nullptr;
   double* dst[7] = {out.tbtotal, out.tbatm, out.tmr, out.tauwet, out.taudry, out.tauliq, out.tauice};
   double* mono[7];
-  for (int i = 0; i < 7; ++i) mono[i] = (pl->C > 0) ? (dst[i] ? w.mono[i] : nullptr) : dst[i];
-  rc = rte_launch(P, L, F, A, in.tk, w.awet, w.adry, cloudy ? w.aliq : nullptr,
-                  cloudy ? w.aice : nullptr, rt ? w.ds : nullptr, in.z, pl->d_amass, pl->d_frq,
-                  (pl->flags & MWRT_F_FROM_SAT) ? 1 : 0, pl->emis, mono[0], mono[1], mono[2], mono[3],
-                  mono[4], mono[5], mono[6], tl, 0, out.status,
+  for (int i = 0; i < 7; ++i) mono[i] = (pl->C > 0 && !fused) ? (dst[i] ? w.mono[i] : nullptr) : dst[i];
+  RteArgs g{};
+  g.P = P; g.L = L; g.F = F; g.A = A;
+  g.tk = in.tk; g.awet = w.awet; g.adry = w.adry;
+  g.denliq = cloudy ? in.denliq : nullptr;
+  g.denice = cloudy ? in.denice : nullptr;
+  g.liq_model = pl->model.liq_model;
+  g.ds = rt ? w.ds : nullptr;
+  g.z = in.z; g.amass = pl->d_amass; g.frq = pl->d_frq; g.emis = pl->emis;
+  g.tbtotal = mono[0]; g.tbatm = mono[1]; g.tmr = mono[2]; g.tauwet = mono[3]; g.taudry = mono[4];
+  g.tauliq = mono[5]; g.tauice = mono[6];
+  g.tau_layer = tl; g.tl_angle = 0; g.status = out.status;
+  if (fused) { g.bpC = pl->C; g.bpS = pl->S; g.bpCpb = pl->bp_cpb; g.bpw = pl->d_bpw; }
+  nvtxRangePushA("mwrt:rte");
+  rc = rte_launch(g, (pl->flags & MWRT_F_FROM_SAT) ? 1 : 0,
                   (pl->C > 0) ? Fanout{MWRT_OUT_PLAIN, 0, {0}} : pl->fanout, st_rte);
+  nvtxRangePop();
   if (rc) return rc;
-  if (pl->C > 0)
+  if (pl->C > 0 && !fused)
     for (int i = 0; i < 7; ++i)
       if (dst[i]) {
         rc = bandpass_launch(P, pl->C, pl->S, A, mono[i], pl->d_bpw, dst[i], pl->fanout, st_rte);
         if (rc) return rc;
       }
+  if (out.tmrcld) {   // rare: upstream's `tmrcld` column (checked by check_io: no band-pass, downwelling)
+    g.bpC = 0;
+    rc = tmrcld_launch(g, in.cld_ibase, in.cld_itop, out.tmrcld, st_rte);
+    if (rc) return rc;
+  }
   if (two) {
     MWRT_CUDA_OK(cudaEventRecord(w.ev_rte, st_rte));
     w.used = true;
@@ -503,6 +583,12 @@ static int check_io(const mwrt_plan* pl, int P, const mwrt_profiles* in, const m
     return fail_arg(MWRT_E_ARG, "forward: MWRT_F_CLOUDY needs denliq and denice");
   if (out->tau_layer && !(pl->flags & MWRT_F_TAU_LAYERS))
     return fail_arg(MWRT_E_ARG, "forward: tau_layer needs MWRT_F_TAU_LAYERS");
+  if (out->tmrcld) {
+    if (!in->cld_ibase || !in->cld_itop)
+      return fail_arg(MWRT_E_ARG, "forward: tmrcld needs cld_ibase and cld_itop");
+    if (pl->C > 0 || (pl->flags & MWRT_F_FROM_SAT))
+      return fail_arg(MWRT_E_ARG, "forward: tmrcld is defined for downwelling, monochromatic runs only");
+  }
   return 0;
 }
 
@@ -513,6 +599,11 @@ static mwrt_profiles offset_in(const mwrt_profiles& in, size_t off) {
   if (r.denice) r.denice += off;
   return r;
 }
+static mwrt_profiles offset_in_p(mwrt_profiles r, size_t off_p) {   // the per-profile (P,) members
+  if (r.cld_ibase) r.cld_ibase += off_p;
+  if (r.cld_itop) r.cld_itop += off_p;
+  return r;
+}
 static mwrt_outputs offset_out(const mwrt_outputs& o, size_t off_pfa, size_t off_pfl, size_t off_p) {
   mwrt_outputs r = o;
   double** f[7] = {&r.tbtotal, &r.tbatm, &r.tmr, &r.tauwet, &r.taudry, &r.tauliq, &r.tauice};
@@ -520,6 +611,7 @@ static mwrt_outputs offset_out(const mwrt_outputs& o, size_t off_pfa, size_t off
     if (*f[i]) *f[i] += off_pfa;
   if (r.tau_layer) r.tau_layer += off_pfl;
   if (r.status) r.status += off_p;
+  if (r.tmrcld) r.tmrcld += off_pfa;
   return r;
 }
 
@@ -539,7 +631,7 @@ int mwrt_plan_forward_device(mwrt_plan* pl, int P, const mwrt_profiles* in, cons
   int c = 0;
   for (int p0 = 0; p0 < P; p0 += chunk, ++c) {
     const int n = std::min(chunk, P - p0);
-    rc = forward_chunk(pl, two ? (c & 1) : 0, n, offset_in(*in, (size_t)p0 * pl->L),
+    rc = forward_chunk(pl, two ? (c & 1) : 0, n, offset_in_p(offset_in(*in, (size_t)p0 * pl->L), p0),
                        offset_out(*out, (size_t)p0 * Fo * pl->A, (size_t)p0 * pl->F * pl->L, p0), st,
                        two ? pl->s_aux : st);
     if (rc) return rc;
@@ -602,6 +694,8 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
   if (rc) return rc;
   if (pl->fanout.mode != MWRT_OUT_PLAIN)
     return fail_arg(MWRT_E_ARG, "mwrt_plan_forward_host: output fan-out is a device-entry feature");
+  if (out->tmrcld)
+    return fail_arg(MWRT_E_ARG, "mwrt_plan_forward_host: tmrcld is a device-entry feature");
   const int L = pl->L, F = pl->F, A = pl->A;
   const int Fo = pl->C > 0 ? pl->C : F;
   const bool cloudy = pl->flags & MWRT_F_CLOUDY;
@@ -640,8 +734,17 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
   const int nin = cloudy ? 6 : 4;
   int ik0, ik1, ok0, ok1;
   ptrdiff_t istride = 0, ostride = 0;
-  const bool in_2d = equally_spaced(hin, nin, ik0, ik1, istride) && ik0 == 0 && ik1 == nin - 1;
-  const bool out_2d = equally_spaced(const_cast<const double* const*>(hout), 7, ok0, ok1, ostride);
+  // one 2-D copy per chunk moves all fields when they are equally spaced -- but only while both
+  // pitches stay within cudaDeviceProp::memPitch (cudaMemcpy2D rejects larger ones: a dense-spectrum
+  // batch can exceed 2 GiB per field); otherwise one cudaMemcpyAsync per field per chunk
+  const size_t max_pitch = pl->mem_pitch ? pl->mem_pitch : (size_t)0x7fffffff;
+  const char* penv = getenv("MWRT_MAX_PITCH");
+  const size_t env_pitch = penv ? (size_t)atoll(penv) : (size_t)0;
+  const size_t pitch_cap = env_pitch ? std::min(env_pitch, max_pitch) : max_pitch;   // MWRT_MAX_PITCH: test hook
+  bool in_2d = equally_spaced(hin, nin, ik0, ik1, istride) && ik0 == 0 && ik1 == nin - 1;
+  bool out_2d = equally_spaced(const_cast<const double* const*>(hout), 7, ok0, ok1, ostride);
+  if (in_2d && ((size_t)istride > pitch_cap || sizeof(double) * in_pitch > pitch_cap)) in_2d = false;
+  if (out_2d && ((size_t)ostride > pitch_cap || sizeof(double) * out_pitch > pitch_cap)) out_2d = false;
 
   // MWRT_TRACE=1: timing events per chunk, timeline printed to stderr after the call (tuning aid)
   static const bool trace = [] { const char* e = getenv("MWRT_TRACE"); return e && atoi(e) != 0; }();
@@ -692,8 +795,8 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
     if (want_tl && c >= 2) MWRT_CUDA_OK(cudaStreamWaitEvent(sc, pl->ev_tl[stl], 0));
     mwrt_profiles din = {pl->h_in + ioff, pl->h_in + in_pitch + ioff, pl->h_in + 2 * in_pitch + ioff,
                          pl->h_in + 3 * in_pitch + ioff, cloudy ? pl->h_in + 4 * in_pitch + ioff : nullptr,
-                         cloudy ? pl->h_in + 5 * in_pitch + ioff : nullptr};
-    mwrt_outputs dout;
+                         cloudy ? pl->h_in + 5 * in_pitch + ioff : nullptr, nullptr, nullptr};
+    mwrt_outputs dout{};
     double** df[7] = {&dout.tbtotal, &dout.tbatm, &dout.tmr, &dout.tauwet, &dout.taudry, &dout.tauliq, &dout.tauice};
     for (int i = 0; i < 7; ++i) *df[i] = hout[i] ? pl->h_out + i * out_pitch + ooff : nullptr;
     dout.tau_layer = want_tl ? pl->h_tl[stl] : nullptr;

@@ -108,67 +108,6 @@ __device__ __forceinline__ double div_fast(double a, double b) {
   return fma(rem, r, q);
 }
 
-// ---- branch-free exp ---------------------------------------------------------------------------
-// exp(x) for |x| < 700 (callers guarantee the range; no NaN/inf/denormal handling).  Cody-Waite
-// reduction by ln2 (k via the 1.5*2^52 rounding constant), degree-13 Taylor on |r| <= ln2/2
-// (truncation 4e-18), scaling by an integer add into the exponent field.  17 FP64-pipe instructions
-// and no branch, so the scheduler can interleave it with neighbouring line-shape arithmetic.
-__device__ __forceinline__ double exp_nb(double x) {
-  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
-  double t = fma(x, 1.4426950408889634, kMagic);
-  const int k = __double2loint(t);
-  t -= kMagic;
-  double r = fma(-t, 6.93147180369123816490e-01, x);
-  r = fma(-t, 1.90821492927058770002e-10, r);
-  double p = 1.6059043836821613e-10;           // 1/13!
-  p = fma(p, r, 2.08767569878681e-09);         // 1/12!
-  p = fma(p, r, 2.505210838544172e-08);        // 1/11!
-  p = fma(p, r, 2.755731922398589e-07);        // 1/10!
-  p = fma(p, r, 2.7557319223985893e-06);       // 1/9!
-  p = fma(p, r, 2.48015873015873e-05);         // 1/8!
-  p = fma(p, r, 1.984126984126984e-04);        // 1/7!
-  p = fma(p, r, 1.388888888888889e-03);        // 1/6!
-  p = fma(p, r, 8.333333333333333e-03);        // 1/5!
-  p = fma(p, r, 4.1666666666666664e-02);       // 1/4!
-  p = fma(p, r, 1.6666666666666666e-01);       // 1/3!
-  p = fma(p, r, 0.5);
-  p = fma(p, r, 1.0);
-  p = fma(p, r, 1.0);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-}
-
-// ---- branch-free natural log ---------------------------------------------------------------------
-// log(x) for normal positive x (callers substitute 1.0 for anything else and select afterwards).
-// x = 2^e * m with m in [sqrt(1/2), sqrt(2)); log m = 2 atanh(s), s = (m-1)/(m+1), |s| <= 0.1716,
-// odd series to s^21 (truncation 2e-17).  ~22 FP64-pipe instructions + 1 MUFU, no branch.
-__device__ __forceinline__ double log_nb(double x) {
-  int hi = __double2hiint(x);
-  const int lo = __double2loint(x);
-  int e = (hi >> 20) - 1023;
-  hi = (hi & 0x000fffff) | 0x3ff00000;            // m in [1, 2)
-  const bool big = hi >= 0x3ff6a09f;              // m >= sqrt(2) (top mantissa bits)
-  hi = big ? hi - 0x00100000 : hi;                // m/2
-  e = big ? e + 1 : e;
-  const double m = __hiloint2double(hi, lo);
-  const double s = (m - 1.0) * rcp_fast(m + 1.0);
-  const double z = s * s;
-  double q = 1.0 / 21.0;
-  q = fma(q, z, 1.0 / 19.0);
-  q = fma(q, z, 1.0 / 17.0);
-  q = fma(q, z, 1.0 / 15.0);
-  q = fma(q, z, 1.0 / 13.0);
-  q = fma(q, z, 1.0 / 11.0);
-  q = fma(q, z, 1.0 / 9.0);
-  q = fma(q, z, 1.0 / 7.0);
-  q = fma(q, z, 1.0 / 5.0);
-  q = fma(q, z, 1.0 / 3.0);
-  const double s2 = s + s;
-  const double ed = (double)e;
-  // e*ln2_hi + (2s + (2s*z*q + e*ln2_lo)); ln2_hi has its low 21 bits clear so e*ln2_hi is exact
-  const double tail = fma(s2 * z, q, ed * 1.90821492927058770002e-10);
-  return fma(ed, 6.93147180369123816490e-01, s2 + tail);
-}
-
 // ---- ordered FP64 ops for the staged helpers (exp_tb_vec, rcp_nr1_vec) ---------------------------------
 // Those evaluate N independent arguments stage by stage, so that the N dependency chains are interleaved
 // in program order (the FP64 pipe needs ~4 independent DFMAs in flight per scheduler).  `asm volatile`
@@ -185,7 +124,7 @@ __device__ __forceinline__ double log_nb(double x) {
 // 256-entry shared-memory table (one LDS.64; the LSU pipe is idle in both hot kernels).  The
 // reduction uses ONE constant, so the result carries a relative error of about |x| * 1.1e-16 on top
 // of ~1 ulp -- the arguments here are optical depths and line-strength exponents of order 1..10.
-// Same domain as exp_nb (|x| < 700, no NaN/inf/denormal handling).
+// Domain: |x| < 700 (callers clamp); no NaN/inf/denormal handling.
 constexpr int kExpTabN = 256;
 static __device__ const double kExpTab[kExpTabN] = {
     0x1.0000000000000p+0, 0x1.00b1afa5abcbfp+0, 0x1.0163da9fb3335p+0, 0x1.02168143b0281p+0,
@@ -312,7 +251,7 @@ __device__ __forceinline__ void exp_tb_vec(const double (&x)[N], double (&y)[N],
 // Table (c_i, -log c_i): c_i ~ 1/m_centre to 12 bits, so r = fma(m, c_i, -1) is exact-rounded and
 // |r| <= 1/128; the two intervals touching 1 use c = 1 (r = m - 1 exactly, table term 0), so the
 // result keeps full RELATIVE accuracy as x -> 1.  log1p(r) to degree 9 (|r| <= 1/64: r^9/10 < 6e-18).
-// Domain: normal positive x (callers substitute a stand-in and select afterwards, like log_nb).
+// Domain: normal positive x (callers substitute a stand-in and select afterwards).
 static __device__ const double kLogTab64[128] = {
     0x1.0000000000000p+0, 0x0.0p+0, 0x1.f440000000000p-1, 0x1.7c61b1cf5dee0p-6,
     0x1.ecc0000000000p-1, 0x1.39f07ba0ebd62p-5, 0x1.e580000000000p-1, 0x1.b35dd9b58baadp-5,
@@ -389,6 +328,39 @@ __device__ __forceinline__ void rcp_nr1_vec(const double (&x)[N], double (&y)[N]
   for (int a = 0; a < N; ++a) MWRT_FMA(y[a], r[a], e[a], r[a]);
 }
 
+// ---- branch-free atan2 ---------------------------------------------------------------------------
+// Principal value of atan2(y, x) for finite (x, y) != (0, 0), no library call, no branch: the ratio
+// t = min(|x|,|y|)/max(|x|,|y|) in [0,1] is reduced around c in {0, 1/2, 1} with
+// atan t = atan c + atan((t-c)/(1+tc)), |u| <= 1/4, and atan u is its odd series to u^27
+// (truncation u^28/29 < 8e-18 relative); quadrants by selects.  ~40 FP64-pipe instructions, <= 2 ulp.
+__device__ __forceinline__ double atan2_nb(double y, double x) {
+  const double ax = fabs(x), ay = fabs(y);
+  const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+  const double t = div_fast(mn, mx);
+  const bool b1 = t > 0.25, b2 = t > 0.75;
+  const double c = b2 ? 1.0 : (b1 ? 0.5 : 0.0);
+  const double ac = b2 ? 0.78539816339744830962 : (b1 ? 0.46364760900080611621 : 0.0);
+  const double u = div_fast(t - c, fma(t, c, 1.0));
+  const double u2 = u * u;
+  double q = -1.0 / 27.0;
+  q = fma(q, u2, 1.0 / 25.0);
+  q = fma(q, u2, -1.0 / 23.0);
+  q = fma(q, u2, 1.0 / 21.0);
+  q = fma(q, u2, -1.0 / 19.0);
+  q = fma(q, u2, 1.0 / 17.0);
+  q = fma(q, u2, -1.0 / 15.0);
+  q = fma(q, u2, 1.0 / 13.0);
+  q = fma(q, u2, -1.0 / 11.0);
+  q = fma(q, u2, 1.0 / 9.0);
+  q = fma(q, u2, -1.0 / 7.0);
+  q = fma(q, u2, 1.0 / 5.0);
+  q = fma(q, u2, -1.0 / 3.0);
+  double r = ac + fma(u * u2, q, u);
+  r = (ay > ax) ? 1.57079632679489661923 - r : r;
+  r = (x < 0.0) ? 3.14159265358979323846 - r : r;
+  return (y < 0.0) ? -r : r;
+}
+
 // ---- minimal complex arithmetic (speed-dependent line shape, liquid permittivity) -----------
 struct cplx {
   double re, im;
@@ -413,7 +385,6 @@ __device__ __forceinline__ cplx cdiv(cplx a, cplx b) {
     return cplx{(a.re * r + a.im) * d, (a.im * r - a.re) * d};
   }
 }
-__device__ __forceinline__ cplx clog_(cplx z) { return cplx{log(hypot(z.re, z.im)), atan2(z.im, z.re)}; }
 
 // Goff-Gratch saturation vapour pressure over water [mb] (RTEquation.vapor), with the
 // table-driven exp/log (10^x = exp(x ln 10), log10 y = ln y / ln 10) instead of libm's exp10/log10 and

@@ -87,10 +87,12 @@ __global__ void k_math_selftest(const int op, const long long n, const double* _
   const double v = x[i];
   double r;
   switch (op) {
-    case MWRT_MATH_EXP_NB: r = exp_nb(v); break;
     case MWRT_MATH_EXP_TB: r = exp_tb(v, etab); break;
-    case MWRT_MATH_LOG_NB: r = log_nb(v); break;
     case MWRT_MATH_LOG_TB: r = log_tb(v, ltab); break;
+    case MWRT_MATH_ATAN2_X1: r = atan2_nb(v, 1.0); break;
+    case MWRT_MATH_ATAN2_XM1: r = atan2_nb(v, -1.0); break;
+    case MWRT_MATH_ATAN2_1X: r = atan2_nb(1.0, v); break;
+    case MWRT_MATH_ATAN2_M1X: r = atan2_nb(-1.0, v); break;
     case MWRT_MATH_RCP: r = rcp_fast(v); break;
     case MWRT_MATH_RCP_SEED: r = rcp_seed(v); break;
     case MWRT_MATH_RCP_NR1: r = rcp_nr1(v); break;

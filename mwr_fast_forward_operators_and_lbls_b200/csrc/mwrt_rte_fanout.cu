@@ -5,14 +5,8 @@
 
 namespace mwrt {
 
-int rte_launch_fanout(int P, int L, int F, int A, const double* tk, const double* awet, const double* adry,
-                      const double* aliq, const double* aice, const double* ds, const double* z,
-                      const double* amass, const double* frq, int from_sat, double emis, double* tbtotal,
-                      double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
-                      double* tauice, double* tau_layer, int tl_angle, int* status, const Fanout& fo,
-                      cudaStream_t st) {
-  return rte_launch_t<true>(P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, from_sat, emis, tbtotal,
-                            tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, fo, st);
+int rte_launch_fanout(const RteArgs& g, int from_sat, const Fanout& fo, cudaStream_t st) {
+  return rte_launch_t<true>(g, from_sat, fo, st);
 }
 
 }  // namespace mwrt

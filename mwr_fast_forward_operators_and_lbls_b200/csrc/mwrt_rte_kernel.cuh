@@ -2,13 +2,11 @@
 // result stores) and mwrt_rte_fanout.cu (stores fanned out to other GPUs) so the two template families
 // compile side by side.
 //
-// mwrt_rte.cu -- kernels 2 and 3: slant path and the radiative-transfer integral.
-//
-// Kernel 2 (k_slant_path): RTEquation.refractivity + RTEquation.ray_tracing, or the plane-parallel
-//   diff(z)/sin(elev) the reference actually runs (the 6-argument constructor at
-//   /root/reference/python_src/proc/PyRTlib_processing.py:123 keeps ray_tracing=False).  SURVEY.md A.9.
 // Kernel 3 (k_rte): RTEquation.exponential_integration (layer optical depths), RTEquation.planck
-//   (downwelling recursion + cosmic background, or upwelling) and RTEquation.bright.  SURVEY.md A.8/A.10.
+//   (downwelling recursion + cosmic background, or upwelling), RTEquation.bright, the cloud
+//   liquid/ice absorption of the cloudy levels (RTEquation.cloudy_absorption, evaluated inline) and the
+//   channel band-pass average.  SURVEY.md A.7/A.8/A.10; reached by the reference through `rte.execute()`
+//   at /root/reference/python_src/proc/PyRTlib_processing.py:126.
 //
 // Mapping: thread = (profile, frequency); it walks the layers once, in the oracle's order, and carries
 // NA viewing angles in registers -- the layer-mean absorption (2-4 log) and the Planck term (1 exp)
@@ -17,11 +15,11 @@
 // is carried as a running product instead of PyRTlib's second exp(-tauprof).
 #pragma once
 #include "mwrt_common.cuh"
+#include "mwrt_cloud.cuh"
+#include "mwrt_rte_args.h"
 #include <type_traits>
 
 namespace mwrt {
-
-constexpr int kRteThreads = 128;
 
 // One layer of exponential_integration without the ds factor: x0 = lower level,
 // x1 = upper level.  Branch-free (selects) so the caller's layer loop stays one basic block:
@@ -33,7 +31,7 @@ __device__ __forceinline__ double layer_mean(double x0, double x1, bool zeroflg,
   const bool close = fabs(x1 - x0) < 1e-09;
   const bool zero = (x0 == 0.0) || (x1 == 0.0);
   const bool use_log = !(negv || close || zero) && (x0 > 0.0) && (x1 > 0.0);  // false for NaN too
-  const double a = use_log ? x1 : 2.0, bq = use_log ? x0 : 1.0;              // keeps log_nb's domain
+  const double a = use_log ? x1 : 2.0, bq = use_log ? x0 : 1.0;              // keeps log_tb's domain
   // reciprocal-multiply (<= 1.5 ulp each) instead of corrected divisions: 4 FP64 instructions fewer
   const double lm = (x1 - x0) * rcp_fast(log_tb(a * rcp_fast(bq), ltab));
   double r = zero ? (zeroflg ? (x1 + x0) * 0.5 : 0.0) : lm;
@@ -48,10 +46,6 @@ __device__ __forceinline__ double layer_mean(double x0, double x1, bool zeroflg,
 __device__ __forceinline__ double planck_mod(double hvk, double t, const double* __restrict__ etab) {
   const double x = hvk * rcp_fast(t);
   return rcp_fast(exp_tb(fmax(fmin(x, 700.0), -700.0), etab) - 1.0);
-}
-__device__ __forceinline__ double bright(double hvk, double b) {
-  if (b > 0.0 || isnan(b)) return hvk / log(1.0 + 1.0 / b);
-  return 0.0;
 }
 // bright() without library calls or branches: b <= 0 -> 0, NaN -> NaN, else hvk / log(1 + 1/b)
 __device__ __forceinline__ double bright_nb(double hvk, double b, const double* __restrict__ ltab) {
@@ -73,50 +67,95 @@ __device__ __forceinline__ double layer_mean_pos(double x0, double x1, const dou
 // a per-angle air-mass table (no ds array, no slant-path kernel); otherwise ds is read from (P,A,L).
 // FROM_SAT (upwelling, levels walked top-down) is a template parameter so the lower/upper level of a
 // layer is chosen at compile time instead of by per-layer selects.
-// measured on B200 (profiles/r01b_*): the plane-parallel variant is fastest capped at 128 registers
-// (4 CTAs/SM); the general variant spills there and runs best uncapped
+// measured on B200 (profiles/r01b_*): the plane-parallel variant is fastest capped at 168 registers
+// (3 CTAs/SM).
 #ifndef MWRT_RTE_MINB
 #define MWRT_RTE_MINB 3
 #endif
-// FANOUT selects the result-store form at compile time (plain stores, or the warp-staged stores that
-// fan out to other GPUs): the staged epilogue costs the plain kernel nothing, not even uniform registers.
-template <int NA, bool CLOUDY, bool PLANE, bool FROM_SAT, bool FANOUT>
 #ifndef MWRT_RTE_MINB_CLOUDY
 #define MWRT_RTE_MINB_CLOUDY 3   // measured: 168 registers without spills, config 3 share -1 %
 #endif
 #ifndef MWRT_RTE_MINB_NA1
 #define MWRT_RTE_MINB_NA1 MWRT_RTE_MINB
 #endif
-__global__ void __launch_bounds__(kRteThreads, !PLANE ? 1 : (CLOUDY ? MWRT_RTE_MINB_CLOUDY
-                                                             : (NA <= 2 ? MWRT_RTE_MINB_NA1 : MWRT_RTE_MINB)))
-k_rte(const int P, const int L, const int F, const int A, const double* __restrict__ tk,
-      const double* __restrict__ awet, const double* __restrict__ adry,
-      const double* __restrict__ aliq, const double* __restrict__ aice,
-      const double* __restrict__ ds, const double* __restrict__ z,
-      const double* __restrict__ amass_tab, const double* __restrict__ frq,
-      const double emis, double* __restrict__ tbtotal, double* __restrict__ tbatm,
-      double* __restrict__ tmr, double* __restrict__ tauwet, double* __restrict__ taudry,
-      double* __restrict__ tauliq, double* __restrict__ tauice, double* __restrict__ tau_layer,
-      const int tl_angle, int* __restrict__ status, const Fanout fo) {
+#ifndef MWRT_RTE_MINB_GENERAL
+#define MWRT_RTE_MINB_GENERAL 3  // ray-traced path: per-angle wet and total sums live in registers
+#endif
+// FANOUT selects the result-store form at compile time (plain stores, or the warp-staged stores that
+// fan out to other GPUs): the staged epilogue costs the plain kernel nothing, not even uniform registers.
+// BP: the channel band-pass average (BASELINE.json config 3) is reduced INSIDE the kernel.  A CTA then
+// covers `cpb` whole channels of one profile (thread = one sub-frequency, <= kRteBpMaxThreads threads);
+// after the layer walk each field goes through shared memory once and thread (channel, angle) adds its
+// S sub-frequencies in index order with one fma each -- the same chain the separate k_bandpass runs, so
+// the result is bit-identical and deterministic, and no monochromatic (P,F,A) field ever reaches HBM.
+template <int NA, bool CLOUDY, bool PLANE, bool FROM_SAT, bool FANOUT, bool BP>
+__global__ void __launch_bounds__(BP ? kRteBpMaxThreads : kRteThreads,
+                                  BP ? 1 : (!PLANE ? MWRT_RTE_MINB_GENERAL
+                                                   : (CLOUDY ? MWRT_RTE_MINB_CLOUDY
+                                                             : (NA <= 2 ? MWRT_RTE_MINB_NA1 : MWRT_RTE_MINB))))
+k_rte(const RteArgs g, const Fanout fo) {
+  const int P = g.P, L = g.L, F = g.F, A = g.A;
+  const double* __restrict__ tk = g.tk;
+  const double* __restrict__ awet = g.awet;
+  const double* __restrict__ adry = g.adry;
+  const double* __restrict__ aliq = g.aliq;
+  const double* __restrict__ aice = g.aice;
+  const double* __restrict__ ds = g.ds;
+  const double* __restrict__ z = g.z;
+  const double* __restrict__ amass_tab = g.amass;
+  const double* __restrict__ frq = g.frq;
+  const double emis = g.emis;
+  double* __restrict__ tbtotal = g.tbtotal;
+  double* __restrict__ tbatm = g.tbatm;
+  double* __restrict__ tmr = g.tmr;
+  double* __restrict__ tauwet = g.tauwet;
+  double* __restrict__ taudry = g.taudry;
+  double* __restrict__ tauliq = g.tauliq;
+  double* __restrict__ tauice = g.tauice;
+  double* __restrict__ tau_layer = g.tau_layer;
+  const int tl_angle = g.tl_angle;
+  int* __restrict__ status = g.status;
+
   __shared__ double etab[kExpTabN];        // exp_tb / log_tb tables (mwrt_common.cuh)
   __shared__ __align__(16) double ltab[128];
   exp_tab_stage(etab);
   log_tab_stage(ltab);
   __syncthreads();
   // threads past the end of the (profile, frequency) range redo the last valid pair and store
-  // nothing: every lane stays alive for the warp-cooperative result stores at the end
-  const long long idx_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // nothing: every lane stays alive for the cooperative result stores at the end
   const long long npf = (long long)P * F;
-  const bool active = idx_raw < npf;
-  const long long idx = active ? idx_raw : npf - 1;
-  const long long p = idx / F;
-  const int jf = (int)(idx - p * F);
+  long long idx_raw, p;
+  int jf, bp_c = 0;
+  bool active;
+  if constexpr (BP) {
+    const int ngrp = (g.bpC + g.bpCpb - 1) / g.bpCpb;
+    p = blockIdx.x / ngrp;
+    const int cl = threadIdx.x / g.bpS;
+    bp_c = (int)(blockIdx.x - p * ngrp) * g.bpCpb + cl;
+    active = (cl < g.bpCpb) && (bp_c < g.bpC);
+    jf = active ? bp_c * g.bpS + (threadIdx.x - cl * g.bpS) : F - 1;
+    idx_raw = p * F + jf;
+  } else {
+    idx_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    active = idx_raw < npf;
+    const long long idc = active ? idx_raw : npf - 1;
+    p = idc / F;
+    jf = (int)(idc - p * F);
+  }
+  const long long idx = p * F + jf;
   const int a0 = blockIdx.y * NA;
   const long long row = idx * (long long)L;  // (p*F + jf)*L
   const double* tkp = tk + p * L;
   const double* zp = PLANE ? z + p * L : nullptr;
   const double* dsp = PLANE ? nullptr : ds + (p * A + a0) * (long long)L;
-  const double hvk = (frq[jf] * 1e9) * kPlanckH / kBoltzmannK;
+  const double fq = frq[jf];
+  const double hvk = (fq * 1e9) * kPlanckH / kBoltzmannK;
+  // cloud absorption evaluated inline (no (P,F,L) liquid/ice arrays): lanes of a warp are frequencies
+  // of ONE profile, so "this level holds liquid" is warp-uniform
+  const bool cld_inline = CLOUDY && (aliq == nullptr);
+  const double* __restrict__ dlq = cld_inline ? g.denliq + p * L : nullptr;
+  const double* __restrict__ dic = cld_inline ? g.denice + p * L : nullptr;
+  const double ice_c = CLOUDY ? ice_coef(fq) : 0.0;
 
   double batm[NA], trans[NA], amass[NA];  // (amass in shared memory measured slower)
   // species sums: per angle in the general case, one zenith-path sum (scaled at the end) if PLANE
@@ -165,9 +204,19 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     Lvl v;
     v.w = awet[row + lv];
     v.d = adry[row + lv];
-    v.l = CLOUDY ? aliq[row + lv] : 0.0;
-    v.i = CLOUDY ? aice[row + lv] : 0.0;
     v.t = tkp[lv];
+    v.l = 0.0;
+    v.i = 0.0;
+    if (CLOUDY) {
+      if (cld_inline) {
+        const double dl = dlq[lv], di = dic[lv];
+        if (dl > 0.0 || isnan(dl)) v.l = liq_abs_unit(g.liq_model, v.t, fq, etab, ltab) * dl;
+        if (di > 0.0 || isnan(di)) v.i = ice_abs_c(ice_c, di);
+      } else {
+        v.l = aliq[row + lv];
+        v.i = aice[row + lv];
+      }
+    }
     v.z = PLANE ? zp[lv] - zref : 0.0;
     return v;
   };
@@ -246,11 +295,12 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
       }
       if (want_tl && active) tau_layer[row + j] = t0 * tl_amass;
     } else {
+      // per-angle sums: wet (+ liquid, ice) and the total; the dry sum is total - the others at the end
+      // (one subtraction per output instead of NA fused multiply-adds per layer and NA live registers)
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
         const double dsa = (a0 + a < A) ? dsp[(long long)a * L + j] : 0.0;
         sw[a] = fma(xw, dsa, sw[a]);
-        sd[a] = fma(xd, dsa, sd[a]);
         if (CLOUDY) { sl[a] = fma(xl, dsa, sl[a]); si[a] = fma(xi, dsa, si[a]); }
         tau[a] = xtot * dsa;
         tauprof[a] += tau[a];
@@ -328,119 +378,142 @@ k_rte(const int P, const int L, const int F, const int A, const double* __restri
     return bad ? qn : bright_nb(hvk, (et >= 0.0) ? batm[a] * rcp_fast(1.0 - et) : batm[a], ltab);
   };
 
-  // Result stores.  A thread owns A consecutive doubles per field, so a warp owns 32*A consecutive
-  // doubles: when this kernel covers all angles (A == NA) and the field is 16-byte aligned, the warp
-  // transposes them through its private slice of shared memory and writes 16 bytes per lane, fully
-  // coalesced -- which is what makes the NVLink multicast form (Fanout mode 1: one `multimem.st.v2`
-  // per 16 bytes, replicated to every GPU by NVSwitch) as cheap as a local store.  Otherwise each
-  // value is stored on its own.
-  // (staging is per HALF warp, 16 threads x NA doubles at a time: 5 KB per CTA instead of 10 keeps the
-  // shared-memory carve-out of the SM at 32 KB; the kernel's strided row reads live on the L1)
-  // The staging slice is DYNAMIC shared memory, present only when the stores fan out to other GPUs:
-  // with plain stores the kernel keeps its small static footprint (and the larger L1) and stores each
-  // value directly, which the L2 merges well enough.
-  extern __shared__ __align__(16) double stage[];   // (kRteThreads / 2) * NA + 2 doubles, or none
-  constexpr bool staged = FANOUT;
+  // Result stores.
+  //  plain   a thread owns A consecutive doubles per field and stores each value directly (the L2
+  //          merges them well enough);
+  //  FANOUT  a warp owns 32*A consecutive doubles: when this kernel covers all angles (A == NA) and the
+  //          field is 16-byte aligned, the warp transposes them through its private slice of shared
+  //          memory (per HALF warp: 5 KB per CTA) and writes 16 bytes per lane, fully coalesced --
+  //          which is what makes the NVLink multicast form (Fanout mode 1: one `multimem.st.v2` per 16
+  //          bytes, replicated to every GPU by NVSwitch) as cheap as a local store;
+  //  BP      every field goes through the CTA's staging area once and thread (channel, angle) adds the
+  //          S sub-frequencies of its channel in index order.
+  // The staging memory is DYNAMIC shared memory, present only for FANOUT / BP.
+  extern __shared__ __align__(16) double stage[];   // FANOUT: (kRteThreads / 2) * NA + 2 doubles; BP: NA * blockDim.x
   const int lane = threadIdx.x & 31;
   double* wst = stage + ((threadIdx.x - lane) / 2) * NA;
   const long long widx0 = idx_raw - lane;                                  // first pair of this warp
   const long long obase = idx * (long long)A + a0;
   auto emit = [&](double* __restrict__ field, auto value) {
     if (!field) return;
-    if constexpr (!FANOUT) {
+    if constexpr (BP) {
+      const int T = blockDim.x, S = g.bpS, C = g.bpC;
+      __syncthreads();            // the previous field's readers are done with the staging area
+#pragma unroll
+      for (int a = 0; a < NA; ++a) stage[a * T + threadIdx.x] = value(a);   // angle-major: conflict-free
+      __syncthreads();
+      const int c0 = bp_c - (int)(threadIdx.x / S);                        // first channel of this CTA
+      for (int r = threadIdx.x; r < g.bpCpb * NA; r += T) {
+        const int cl = r / NA, a = r - cl * NA, c = c0 + cl;
+        if (c < C && a0 + a < A) {
+          const double* src = stage + a * T + cl * S;
+          const double* w = g.bpw ? g.bpw + (long long)c * S : nullptr;
+          double acc = 0.0;
+          for (int sidx = 0; sidx < S; ++sidx) acc = fma(w ? w[sidx] : 1.0 / S, src[sidx], acc);
+          field[((long long)p * C + c) * A + a0 + a] = acc;
+        }
+      }
+    } else if constexpr (!FANOUT) {
       if (active) {
 #pragma unroll
         for (int a = 0; a < NA; ++a)
           if (a0 + a < A) field[obase + a] = value(a);
       }
     } else {
-    const bool coalesced = (A == NA) && ((reinterpret_cast<unsigned long long>(field) & 15ull) == 0);
+      const bool coalesced = (A == NA) && ((reinterpret_cast<unsigned long long>(field) & 15ull) == 0);
 #pragma unroll 1
-    for (int h = 0; h < 2; ++h) {
-      // the 16 threads of half h put their NA values into the warp's slice
-      if ((lane >> 4) == h) {
+      for (int h = 0; h < 2; ++h) {
+        // the 16 threads of half h put their NA values into the warp's slice
+        if ((lane >> 4) == h) {
 #pragma unroll
-        for (int a = 0; a < NA; ++a) wst[(lane & 15) * NA + a] = value(a);
-      }
-      __syncwarp();
-      const long long hidx0 = widx0 + 16 * h;                              // first pair of this half
-      const long long hleft = npf - hidx0;
-      const int nval = (int)(hleft >= 16 ? 16 : (hleft > 0 ? hleft : 0)) * NA;   // valid doubles
-      if (coalesced) {
-        double* dst = field + hidx0 * NA;
-        const int npeer = (fo.mode == MWRT_OUT_PEERS) ? fo.n : 1;
+          for (int a = 0; a < NA; ++a) wst[(lane & 15) * NA + a] = value(a);
+        }
+        __syncwarp();
+        const long long hidx0 = widx0 + 16 * h;                              // first pair of this half
+        const long long hleft = npf - hidx0;
+        const int nval = (int)(hleft >= 16 ? 16 : (hleft > 0 ? hleft : 0)) * NA;   // valid doubles
+        if (coalesced) {
+          double* dst = field + hidx0 * NA;
+          const int npeer = (fo.mode == MWRT_OUT_PEERS) ? fo.n : 1;
 #pragma unroll 1
-        for (int r = 0; r < npeer; ++r) {
-          double* d = (fo.mode == MWRT_OUT_PEERS)
-                          ? reinterpret_cast<double*>(reinterpret_cast<char*>(dst) + fo.off[r]) : dst;
+          for (int r = 0; r < npeer; ++r) {
+            double* d = (fo.mode == MWRT_OUT_PEERS)
+                            ? reinterpret_cast<double*>(reinterpret_cast<char*>(dst) + fo.off[r]) : dst;
 #pragma unroll 1
-          for (int g = 2 * lane; g < nval; g += 64) {
-            const double v0 = wst[g], v1 = wst[g + 1];     // slice is padded by one pair
-            if (g + 1 < nval) {
-              if (fo.mode == MWRT_OUT_MULTICAST) out_store2_mc(d + g, v0, v1);
-              else *reinterpret_cast<double2*>(d + g) = make_double2(v0, v1);
-            } else {
-              if (fo.mode == MWRT_OUT_MULTICAST) out_store_mc(d + g, v0);
-              else d[g] = v0;
+            for (int gq = 2 * lane; gq < nval; gq += 64) {
+              const double v0 = wst[gq], v1 = wst[gq + 1];     // slice is padded by one pair
+              if (gq + 1 < nval) {
+                if (fo.mode == MWRT_OUT_MULTICAST) out_store2_mc(d + gq, v0, v1);
+                else *reinterpret_cast<double2*>(d + gq) = make_double2(v0, v1);
+              } else {
+                if (fo.mode == MWRT_OUT_MULTICAST) out_store_mc(d + gq, v0);
+                else d[gq] = v0;
+              }
             }
           }
-        }
-      } else if (active && (lane >> 4) == h) {
+        } else if (active && (lane >> 4) == h) {
 #pragma unroll 1
-        for (int a = 0; a < NA; ++a)
-          if (a0 + a < A) out_store(field + obase + a, wst[(lane & 15) * NA + a], fo);
+          for (int a = 0; a < NA; ++a)
+            if (a0 + a < A) out_store(field + obase + a, wst[(lane & 15) * NA + a], fo);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
-    }   // FANOUT
   };
   emit(tbtotal, v_tot);
   emit(tbatm, v_atm);
   emit(tmr, v_mr);
   emit(tauwet, [&](int a) { return bad ? qn : (PLANE ? sw[0] * amass[a] : sw[a]); });
-  emit(taudry, [&](int a) { return bad ? qn : (PLANE ? sd[0] * amass[a] : sd[a]); });
+  emit(taudry, [&](int a) {
+    return bad ? qn : (PLANE ? sd[0] * amass[a] : (CLOUDY ? tauprof[a] - sw[a] - sl[a] - si[a] : tauprof[a] - sw[a]));
+  });
   emit(tauliq, [&](int a) { return bad ? qn : (PLANE ? sl[0] * amass[a] : sl[a]); });
   emit(tauice, [&](int a) { return bad ? qn : (PLANE ? si[0] * amass[a] : si[a]); });
 }
 
 template <int NA, bool FANOUT>
-static int launch_rte_na(bool cloudy, int P, int L, int F, int A, const double* tk,
-                         const double* awet, const double* adry, const double* aliq,
-                         const double* aice, const double* ds, const double* z, const double* amass,
-                         const double* frq, int from_sat, double emis, double* tbtotal,
-                         double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
-                         double* tauice, double* tau_layer, int tl_angle, int* status,
-                         const Fanout& fo, cudaStream_t st) {
-  const long long n = (long long)P * F;
-  dim3 grid((unsigned)((n + kRteThreads - 1) / kRteThreads), (unsigned)((A + NA - 1) / NA));
-#define MWRT_K_ARGS P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, fo
-#define MWRT_K_LAUNCH(C_, P_)                                                                   \
-  do {                                                                                          \
-    if (from_sat) k_rte<NA, C_, P_, true, FANOUT><<<grid, kRteThreads, dsm, st>>>(MWRT_K_ARGS); \
-    else k_rte<NA, C_, P_, false, FANOUT><<<grid, kRteThreads, dsm, st>>>(MWRT_K_ARGS);         \
-  } while (0)
-  const bool plane = (ds == nullptr);
+static int launch_rte_na(const RteArgs& g, bool cloudy, int from_sat, const Fanout& fo, cudaStream_t st) {
+  const long long n = (long long)g.P * g.F;
+  const bool plane = (g.ds == nullptr);
+  const unsigned gy = (unsigned)((g.A + NA - 1) / NA);
+  if constexpr (!FANOUT) {
+    if (g.bpC > 0) {   // fused band-pass: plane-parallel, plain stores (checked by rte_launch)
+      const int ngrp = (g.bpC + g.bpCpb - 1) / g.bpCpb;
+      const int threads = ((g.bpCpb * g.bpS + 31) / 32) * 32;
+      dim3 grid((unsigned)((long long)g.P * ngrp), gy);
+      const size_t dsm = sizeof(double) * (size_t)threads * NA;
+#define MWRT_K_BP(C_, S_) k_rte<NA, C_, true, S_, false, true><<<grid, threads, dsm, st>>>(g, fo)
+      if (cloudy && from_sat) MWRT_K_BP(true, true);
+      else if (cloudy) MWRT_K_BP(true, false);
+      else if (from_sat) MWRT_K_BP(false, true);
+      else MWRT_K_BP(false, false);
+#undef MWRT_K_BP
+      MWRT_CUDA_OK(cudaGetLastError());
+      return 0;
+    }
+  }
+  dim3 grid((unsigned)((n + kRteThreads - 1) / kRteThreads), gy);
   const size_t dsm = FANOUT ? sizeof(double) * ((kRteThreads / 2) * NA + 2) : 0;
+#define MWRT_K_LAUNCH(C_, P_)                                                                    \
+  do {                                                                                           \
+    if (from_sat) k_rte<NA, C_, P_, true, FANOUT, false><<<grid, kRteThreads, dsm, st>>>(g, fo); \
+    else k_rte<NA, C_, P_, false, FANOUT, false><<<grid, kRteThreads, dsm, st>>>(g, fo);         \
+  } while (0)
   if (cloudy && plane) MWRT_K_LAUNCH(true, true);
   else if (cloudy) MWRT_K_LAUNCH(true, false);
   else if (plane) MWRT_K_LAUNCH(false, true);
   else MWRT_K_LAUNCH(false, false);
 #undef MWRT_K_LAUNCH
-#undef MWRT_K_ARGS
   MWRT_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-// ds != null: general path (P,A,L).  ds == null: plane-parallel, z (P,L) + amass (A,) device arrays.
+// g.ds != null: general path (P,A,L).  g.ds == null: plane-parallel, z (P,L) + amass (A,) device arrays.
+// cloudy = liquid/ice terms present: (aliq, aice) arrays, or (denliq, denice) for inline evaluation.
 template <bool FANOUT>
-static int rte_launch_t(int P, int L, int F, int A, const double* tk, const double* awet, const double* adry,
-               const double* aliq, const double* aice, const double* ds, const double* z,
-               const double* amass, const double* frq, int from_sat, double emis, double* tbtotal,
-               double* tbatm, double* tmr, double* tauwet, double* taudry, double* tauliq,
-               double* tauice, double* tau_layer, int tl_angle, int* status, const Fanout& fo,
-               cudaStream_t st) {
-  const bool cloudy = (aliq != nullptr) && (aice != nullptr);
-#define MWRT_RTE_ARGS cloudy, P, L, F, A, tk, awet, adry, aliq, aice, ds, z, amass, frq, from_sat, emis, tbtotal, tbatm, tmr, tauwet, taudry, tauliq, tauice, tau_layer, tl_angle, status, fo, st
+static int rte_launch_t(const RteArgs& g, int from_sat, const Fanout& fo, cudaStream_t st) {
+  const bool cloudy = (g.aliq != nullptr && g.aice != nullptr) || (g.denliq != nullptr && g.denice != nullptr);
+  const int A = g.A;
   int na;
   if (A <= 1) na = 1;
   else if (A <= 2) na = 2;
@@ -450,15 +523,13 @@ static int rte_launch_t(int P, int L, int F, int A, const double* tk, const doub
   else if (A <= 10) na = 10;
   else na = (((A + 9) / 10) * 10 <= ((A + 7) / 8) * 8) ? 10 : 8;
   switch (na) {
-    case 1: return launch_rte_na<1, FANOUT>(MWRT_RTE_ARGS);
-    case 2: return launch_rte_na<2, FANOUT>(MWRT_RTE_ARGS);
-    case 4: return launch_rte_na<4, FANOUT>(MWRT_RTE_ARGS);
-    case 5: return launch_rte_na<5, FANOUT>(MWRT_RTE_ARGS);
-    case 8: return launch_rte_na<8, FANOUT>(MWRT_RTE_ARGS);
-    default: return launch_rte_na<10, FANOUT>(MWRT_RTE_ARGS);
+    case 1: return launch_rte_na<1, FANOUT>(g, cloudy, from_sat, fo, st);
+    case 2: return launch_rte_na<2, FANOUT>(g, cloudy, from_sat, fo, st);
+    case 4: return launch_rte_na<4, FANOUT>(g, cloudy, from_sat, fo, st);
+    case 5: return launch_rte_na<5, FANOUT>(g, cloudy, from_sat, fo, st);
+    case 8: return launch_rte_na<8, FANOUT>(g, cloudy, from_sat, fo, st);
+    default: return launch_rte_na<10, FANOUT>(g, cloudy, from_sat, fo, st);
   }
-#undef MWRT_RTE_ARGS
 }
-
 
 }  // namespace mwrt

@@ -6,6 +6,8 @@ state) -- so there is no collective inside the computation.  `t
 (NCCL over NVLink 5 / NVSwitch on the GPU box, gloo in the CPU tests) is used only to assemble the
 (P,F,A) results.
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -161,6 +163,111 @@ class PipelinedForward:
     def field(self, name, slot):
         i = self.fields.index(name)
         return self.gathered[slot][:, i].reshape(self.world * self.P_local, self.plan.Fo, self.plan.A)
+
+
+class CopyEngineGather:
+    """The gather on the COPY ENGINES: every rank pushes its finished fields straight into the gathered
+    buffer of each peer with ONE asynchronous device-to-device copy per peer (`mwrt_push_async` =
+    cudaMemcpyAsync onto peer-mapped symmetric memory, one side stream per peer), while the next batch
+    is being computed.  No collective kernel runs, so nothing takes SMs from the two FP64-bound kernels
+    (an NCCL all-gather occupies 16+ CTAs for the whole transfer); a symmetric-memory barrier per step,
+    on the side stream, tells every rank that all pushes of the step have landed.
+
+    Only what carries information travels: in clear sky `tauliq` / `tauice` are identically zero (NaN
+    for flagged profiles) and are rebuilt from the gathered status words by `field()`.
+
+    Kernel 3 writes its results directly into this rank's slot of the symmetric buffer, so there is no
+    local staging copy.  Results of step s: `gathered[s % 2]`, laid out (world, nfield, P_local, F, A)
+    on every rank (double-buffered); `status_g[s % 2]` is (world, P_local).
+
+    Ordering: the pushes of step s+2 overwrite the peers' copy of buffer s % 2, so they wait for the
+    barrier of step s+1 -- every rank arrives there only after the consumers of its step-s results
+    were queued ahead of its step-s+1 kernels.
+    """
+
+    def __init__(self, plan, P_local, fields, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        self.plan, self.fields = plan, tuple(fields)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.P_local = int(P_local)
+        F, A = plan.Fo, plan.A
+        zero = () if plan.cloudy else ("tauliq", "tauice")
+        self.moved = tuple(f for f in self.fields if f not in zero)
+        self.zero_fields = tuple(f for f in self.fields if f in zero)
+        nf = len(self.moved)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        shape = (self.world, nf, self.P_local, F, A)
+        self.gathered = [symm_mem.empty(shape, dtype=torch.float64, device=dev) for _ in range(2)]
+        self.hdl = [symm_mem.rendezvous(g, self.group) for g in self.gathered]
+        self.status_g = [symm_mem.empty((self.world, self.P_local), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.hdl_st = [symm_mem.rendezvous(g, self.group) for g in self.status_g]
+        self.rank_bytes = nf * self.P_local * F * A * 8
+        self.st_bytes = self.P_local * 4
+        # addresses of THIS rank's slot inside every peer's buffers, as mapped into this process
+        self.peers = [q for q in range(self.world) if q != self.rank]
+        self.dst = [{q: int(self.hdl[b].buffer_ptrs[q]) + self.rank * self.rank_bytes for q in self.peers}
+                    for b in range(2)]
+        self.dst_st = [{q: int(self.hdl_st[b].buffer_ptrs[q]) + self.rank * self.st_bytes for q in self.peers}
+                       for b in range(2)]
+        self.push = {q: torch.cuda.Stream() for q in self.peers}
+        self.comm = torch.cuda.Stream()
+        self.computed = [torch.cuda.Event() for _ in range(2)]
+        self.pushed = [{q: torch.cuda.Event() for q in self.peers} for _ in range(2)]
+        self.landed = [torch.cuda.Event() for _ in range(2)]     # barrier of the step using buffer b passed
+        self.step = 0
+
+    def run(self, z, p, t, rh, denliq=None, denice=None):
+        b = self.step % 2
+        main = torch.cuda.current_stream()
+        if self.step >= 2:
+            main.wait_event(self.landed[b])       # my pushes out of slot b (two steps ago) are complete
+        own = self.gathered[b][self.rank]         # (nf, P_local, F, A): kernel 3 writes here directly
+        out = {k: own[i] for i, k in enumerate(self.moved)}
+        out["status"] = self.status_g[b][self.rank]
+        self.plan.forward(z, p, t, rh, denliq, denice, fields=self.moved, out=out)
+        self.computed[b].record(main)
+        src, src_st = own.data_ptr(), self.status_g[b][self.rank].data_ptr()
+        for q in self.peers:
+            st = self.push[q]
+            st.wait_event(self.computed[b])
+            if self.step >= 1:
+                st.wait_event(self.landed[1 - b])  # peers are done with what buffer b held two steps ago
+            h = C.c_void_p(st.cuda_stream)
+            self._lib.check(self.lib.mwrt_push_async(C.c_void_p(self.dst[b][q]), C.c_void_p(src),
+                                                     self.rank_bytes, h), "push_async")
+            self._lib.check(self.lib.mwrt_push_async(C.c_void_p(self.dst_st[b][q]), C.c_void_p(src_st),
+                                                     self.st_bytes, h), "push_async")
+            self.pushed[b][q].record(st)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.computed[b])
+            for q in self.peers:
+                self.comm.wait_event(self.pushed[b][q])
+            self.hdl[b].barrier(channel=b)         # every rank's pushes of this step have landed everywhere
+            self.landed[b].record(self.comm)
+        self.step += 1
+        return b
+
+    def finish(self):
+        torch.cuda.current_stream().wait_stream(self.comm)
+
+    def field(self, name, slot):
+        """(world * P_local, F, A) view of one gathered field, profiles ordered rank-major."""
+        n = self.world * self.P_local
+        if name in self.zero_fields:              # identically zero in clear sky; NaN where flagged
+            out = torch.zeros((n, self.plan.Fo, self.plan.A), dtype=torch.float64, device=self.dev)
+            bad = (self.status_g[slot].reshape(n) & 11) != 0      # NAN_INPUT | NEG_ABS | RANGE
+            out[bad] = float("nan")
+            return out
+        i = self.moved.index(name)
+        return self.gathered[slot][:, i].reshape(n, self.plan.Fo, self.plan.A)
+
+    def status(self, slot):
+        return self.status_g[slot].reshape(self.world * self.P_local)
 
 
 class FusedGatherForward:

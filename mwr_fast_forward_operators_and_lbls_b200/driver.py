@@ -16,6 +16,7 @@ import numpy as np
 
 from . import io_formats
 from .forward import simulate
+from .models import provenance
 from .synth import HATPRO_FRQ
 
 ELEVATIONS = np.array([90., 30, 19.2, 14.4, 11.4, 8.4, 6.6, 5.4, 4.8, 4.2])   # PyRTlib_processing.py:37
@@ -74,12 +75,35 @@ def derive_TBs4PyRTlib(ds, args=None):
     dims ('time','N_Channels','elevation','Crop') and the reference's attrs to `ds` and returns it.
     `ds` is an xarray.Dataset or an io_formats.SimpleDataset."""
     elev = np.asarray(ds["elevation"].values, dtype=np.float64)
-    tbs = derive_tbs_arrays(ds["Level_z"].values, ds["Level_Pressure"].values,
-                            ds["Level_Temperature"].values, ds["Level_RH"].values, elevations=elev)
+    tbs = derive_tbs_arrays(_level_values(ds, "Level_z"), _level_values(ds, "Level_Pressure"),
+                            _level_values(ds, "Level_Temperature"), _level_values(ds, "Level_RH"),
+                            elevations=elev)
     for model, var in io_formats.OUTPUT_VARS:
         ds[var] = (io_formats.TB_DIMS, tbs[model])
-        ds[var].attrs = io_formats.tb_attrs(model)
+        attrs = io_formats.tb_attrs(model)
+        note = provenance(model)
+        if note:     # the built-in line tables are not pinned to PyRTlib: say so in the product
+            attrs["model_tables"] = note
+        ds[var].attrs = attrs
     return ds
+
+
+LEVEL_DIMS = ("N_Levels", "time", "Crop")   # preprocessing4all.py:1195-1203
+
+
+def _level_values(ds, name):
+    """`Level_*` as a (N_Levels, time, Crop) array.  The reference indexes BY NAME
+    (`.isel(time=i).isel(Crop=j)`, PyRTlib_processing.py:109-114), so it does not depend on the stored
+    axis order; a dataset that was transposed or merged time-major is put back in contract order here
+    instead of being unpacked with levels and profiles swapped."""
+    var = ds[name]
+    dims = tuple(getattr(var, "dims", ()) or ())
+    vals = np.asarray(var.values)
+    if not dims or dims == LEVEL_DIMS:
+        return vals
+    if sorted(dims) != sorted(LEVEL_DIMS):
+        raise ValueError("%s has dims %s, expected some order of %s" % (name, dims, LEVEL_DIMS))
+    return np.transpose(vals, [dims.index(d) for d in LEVEL_DIMS])
 
 
 def legacy_sonde_table(z_km, p, t, rh, z_km_crop, p_crop, t_crop, rh_crop):

@@ -55,7 +55,7 @@ class Plan:
     """`mwrt_plan`: fixes (model, L, F, A, frq, angles, flags); owns workspace and streams."""
 
     def __init__(self, model, L, frq, angles, ray_tracing=False, from_sat=False, cloudy=False,
-                 tau_layers=False, chunk_profiles=0, emissivity=1.0, bandpass=None):
+                 tau_layers=False, chunk_profiles=0, emissivity=1.0, bandpass=None, f32_lineshape=False):
         _need_cuda()
         self.lib = _lib.load()
         self.model = get_model(model)
@@ -84,6 +84,9 @@ class Plan:
                 wp = w.ctypes.data_as(_lib.c_dp)
             _lib.check(self.lib.mwrt_plan_set_bandpass(h, int(nchan), int(nsub), wp), "set_bandpass")
             self.Fo = int(nchan)
+        self.f32_lineshape = bool(f32_lineshape)
+        if f32_lineshape:   # fp32 line-shape mode (north_star: <= 0.01 K, reported separately)
+            _lib.check(self.lib.mwrt_plan_set_precision(h, _lib.PREC_F32_LINESHAPE), "set_precision")
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -110,28 +113,52 @@ class Plan:
         return int(self.lib.mwrt_plan_launch_count(self._h, int(P)))
 
     # ---- device buffers in, device buffers out ------------------------------------------------
-    def forward(self, z, p, t, rh, denliq=None, denice=None, fields=FIELDS, out=None):
+    def _check_dev(self, x, P, what):
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
+                and tuple(x.shape) == (P, self.L)):
+            raise ValueError("%s must be a contiguous CUDA fp64 tensor of shape (P,%d)" % (what, self.L))
+
+    def forward(self, z, p, t, rh, denliq=None, denice=None, fields=FIELDS, out=None, cld_ibase=None,
+                cld_itop=None):
         """All arguments (P,L) CUDA fp64 tensors.  Returns dict of (P,Fo,A) CUDA tensors
         (+ 'tau_layer' (P,F,L) if the plan was made with tau_layers, + 'status' (P,) int32).
-        Asynchronous on the current torch stream."""
+        `fields` may name 'tmrcld' (upstream's cloud mean radiating temperature); it needs
+        cld_ibase / cld_itop, (P,) int32 CUDA tensors with the level indices of the cloud's base and top
+        (-1: none).  Asynchronous on the current torch stream."""
         P = z.shape[0]
-        for x in (z, p, t, rh):
-            if not (x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
-                    and tuple(x.shape) == (P, self.L)):
-                raise ValueError("inputs must be contiguous CUDA fp64 tensors of shape (P,%d)" % self.L)
+        for x, what in ((z, "z"), (p, "p"), (t, "t"), (rh, "rh")):
+            self._check_dev(x, P, what)
+        if self.cloudy:
+            if denliq is None or denice is None:
+                raise ValueError("a cloudy plan needs denliq and denice")
+            self._check_dev(denliq, P, "denliq")
+            self._check_dev(denice, P, "denice")
         dev = z.device
+        want_tmrcld = "tmrcld" in fields
+        if want_tmrcld:
+            for x in (cld_ibase, cld_itop):
+                if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.int32
+                        and x.is_contiguous() and tuple(x.shape) == (P,)):
+                    raise ValueError("tmrcld needs cld_ibase and cld_itop: contiguous CUDA int32 tensors (P,)")
         res = out if out is not None else {}
         for f in fields:
             if f not in res:      # (an int entry is a raw / multicast address, see set_output_fanout)
                 res[f] = torch.empty((P, self.Fo, self.A), dtype=torch.float64, device=dev)
+            elif isinstance(res[f], torch.Tensor):
+                if not (res[f].is_cuda and res[f].dtype == torch.float64 and res[f].is_contiguous()
+                        and tuple(res[f].shape) == (P, self.Fo, self.A)):
+                    raise ValueError("out['%s'] must be a contiguous CUDA fp64 tensor of shape (%d,%d,%d)"
+                                     % (f, P, self.Fo, self.A))
         if self.tau_layers and "tau_layer" not in res:
             res["tau_layer"] = torch.empty((P, self.F, self.L), dtype=torch.float64, device=dev)
         if "status" not in res:
             res["status"] = torch.empty((P,), dtype=torch.int32, device=dev)
         pin = _lib.Profiles(_ptr(z), _ptr(p), _ptr(t), _ptr(rh),
-                            _ptr(denliq if self.cloudy else None), _ptr(denice if self.cloudy else None))
-        pout = _lib.Outputs(*[_ptr(res.get(f)) for f in FIELDS], _ptr(res.get("tau_layer")),
-                            _ptr(res["status"]))
+                            _ptr(denliq if self.cloudy else None), _ptr(denice if self.cloudy else None),
+                            _ptr(cld_ibase if want_tmrcld else None), _ptr(cld_itop if want_tmrcld else None))
+        pout = _lib.Outputs(*[_ptr(res.get(f)) for f in FIELDS],
+                            _ptr(res.get("tau_layer")), _ptr(res["status"]),
+                            _ptr(res.get("tmrcld") if want_tmrcld else None))
         with torch.cuda.device(dev):
             _lib.set_device(dev.index if dev.index is not None else torch.cuda.current_device())
             _lib.check(self.lib.mwrt_plan_forward_device(self._h, int(P), C.byref(pin), C.byref(pout),
@@ -153,7 +180,26 @@ class Plan:
         for x in (z, p, t, rh):
             if x.shape != (P, self.L):
                 raise ValueError("inputs must have shape (P,%d)" % self.L)
+        if self.cloudy and (denliq is None or denice is None):
+            raise ValueError("a cloudy plan needs denliq and denice")
+        for x in (denliq, denice):
+            if x is not None and x.shape != (P, self.L):
+                raise ValueError("denliq/denice must have shape (P,%d)" % self.L)
         res = out if out is not None else {}
+        for f in FIELDS:
+            v = res.get(f)
+            if v is None:
+                continue
+            if isinstance(v, torch.Tensor):
+                v = v.numpy()
+            if not (isinstance(v, np.ndarray) and v.dtype == np.float64 and v.flags["C_CONTIGUOUS"]
+                    and v.shape == (P, self.Fo, self.A)):
+                raise ValueError("out['%s'] must be a C-contiguous float64 array of shape (%d,%d,%d)"
+                                 % (f, P, self.Fo, self.A))
+        if "status" in res:
+            v = res["status"].numpy() if isinstance(res["status"], torch.Tensor) else res["status"]
+            if not (v.dtype == np.int32 and v.flags["C_CONTIGUOUS"] and v.shape == (P,)):
+                raise ValueError("out['status'] must be a C-contiguous int32 array of shape (%d,)" % P)
         missing = [f for f in fields if f not in res]
         if missing:   # one pinned block: asynchronous copies, and one 2-D copy per chunk for all fields
             res.update(pinned_fields(missing, (P, self.Fo, self.A)))
@@ -169,8 +215,9 @@ class Plan:
                 return C.c_void_p(x.data_ptr())
             return C.c_void_p(x.ctypes.data)
         pin = _lib.Profiles(hp(z), hp(p), hp(t), hp(rh), hp(denliq if self.cloudy else None),
-                            hp(denice if self.cloudy else None))
-        pout = _lib.Outputs(*[hp(res.get(f)) for f in FIELDS], hp(res.get("tau_layer")), hp(res["status"]))
+                            hp(denice if self.cloudy else None), hp(None), hp(None))
+        pout = _lib.Outputs(*[hp(res.get(f)) for f in FIELDS], hp(res.get("tau_layer")), hp(res["status"]),
+                            hp(None))
         _lib.set_device(torch.cuda.current_device())
         _lib.check(self.lib.mwrt_plan_forward_host(self._h, int(P), C.byref(pin), C.byref(pout)),
                    "forward_host")
@@ -189,7 +236,8 @@ def pinned_fields(names, shape, dtype=np.float64):
 
 
 def simulate(z, p, t, rh, frq, angles, model, ray_tracing=False, from_sat=False, denliq=None,
-             denice=None, fields=FIELDS, tau_layers=False, bandpass=None, device=None):
+             denice=None, fields=FIELDS, tau_layers=False, bandpass=None, device=None,
+             f32_lineshape=False):
     """One-call batched forward model (SURVEY.md 8(b) "batched entry").
 
     z,p,t,rh[,denliq,denice]: (P,L) arrays/tensors, ground-first.  Returns dict of (P,F,A) CUDA
@@ -202,7 +250,7 @@ def simulate(z, p, t, rh, frq, angles, model, ray_tracing=False, from_sat=False,
         denliq = torch.zeros_like(zt) if denliq is None else _dev64(denliq, zt.device)
         denice = torch.zeros_like(zt) if denice is None else _dev64(denice, zt.device)
     plan = Plan(model, zt.shape[1], frq, angles, ray_tracing=ray_tracing, from_sat=from_sat,
-                cloudy=cloudy, tau_layers=tau_layers, bandpass=bandpass)
+                cloudy=cloudy, tau_layers=tau_layers, bandpass=bandpass, f32_lineshape=f32_lineshape)
     res = plan.forward(zt, _dev64(p, zt.device), _dev64(t, zt.device), _dev64(rh, zt.device),
                        denliq, denice, fields=fields)
     torch.cuda.current_stream().synchronize()  # the plan (and its workspace) dies with this frame
@@ -222,8 +270,9 @@ def vapor(t, rh):
     return e, rho
 
 
-def absorption(model, p, t, e, frq, denliq=None, denice=None):
-    """awet, adry[, aliq, aice] as (P,F,L) CUDA tensors + status (P,)."""
+def absorption(model, p, t, e, frq, denliq=None, denice=None, f32_lineshape=False):
+    """awet, adry[, aliq, aice] as (P,F,L) CUDA tensors + status (P,).  f32_lineshape: the fp32
+    line-shape mode (`mwrt_absorption_f32ls`)."""
     _need_cuda()
     lib = _lib.load()
     m = get_model(model)
@@ -240,9 +289,9 @@ def absorption(model, p, t, e, frq, denliq=None, denice=None):
         denice = torch.zeros_like(p) if denice is None else _dev64(denice)
         aliq, aice = torch.empty_like(awet), torch.empty_like(awet)
     status = torch.zeros((P,), dtype=torch.int32, device="cuda")
-    _lib.check(lib.mwrt_absorption_f64(m.handle, P, L, F, _ptr(p), _ptr(t), _ptr(e), _ptr(denliq),
-                                       _ptr(denice), _ptr(f), _ptr(awet), _ptr(adry), _ptr(aliq),
-                                       _ptr(aice), _ptr(status), _stream()), "absorption")
+    fn = lib.mwrt_absorption_f32ls if f32_lineshape else lib.mwrt_absorption_f64
+    _lib.check(fn(m.handle, P, L, F, _ptr(p), _ptr(t), _ptr(e), _ptr(denliq), _ptr(denice), _ptr(f),
+                  _ptr(awet), _ptr(adry), _ptr(aliq), _ptr(aice), _ptr(status), _stream()), "absorption")
     torch.cuda.current_stream().synchronize()
     return dict(awet=awet, adry=adry, aliq=aliq, aice=aice, status=status)
 
@@ -318,7 +367,8 @@ def measure_dfma_peak():
     return fl.value, mhz.value
 
 
-MATH_OPS = {"exp_nb": 0, "exp_tb": 1, "log_nb": 2, "log_tb": 3, "rcp": 4, "rcp_seed": 5, "rcp_nr1": 6}
+MATH_OPS = {"exp_tb": 1, "log_tb": 3, "rcp": 4, "rcp_seed": 5, "rcp_nr1": 6, "atan2_x1": 7, "atan2_xm1": 8,
+            "atan2_1x": 9, "atan2_m1x": 10}
 
 
 def math_selftest(op, x):

@@ -9,6 +9,7 @@ descriptor of the same schema, e.g. the true tables dumped by `baseline/probe_py
 import ctypes as C
 import json
 import os
+import warnings
 
 import numpy as np
 
@@ -57,12 +58,35 @@ def _pack(desc):
     return d, (h2o, o2)  # keep the arrays alive while the C call reads them
 
 
+# Provenance of the built-in tables.  They answer to PyRTlib's model strings but were restated without
+# access to PyRTlib (no network, package absent: DESIGN.md section 2): nothing pins their digits to the
+# upstream line lists, so every user of a built-in model is told once, and the driver records it in the
+# output attributes.  `Model.from_descriptor` with tables dumped from a real PyRTlib carries no flag.
+BUILTIN_TABLES_VERIFIED = False
+PROVENANCE = ("built-in %s tables: restatement of the PyRTlib 1.1.x / Rosenkranz line lists, NOT verified "
+              "against PyRTlib output (mwr_fast_forward_operators_and_lbls_b200/DESIGN.md, 'Oracle')")
+_warned = set()
+
+
+def provenance(name):
+    """One-line provenance note for a model name ('' for descriptors supplied by the caller)."""
+    return PROVENANCE % name if not BUILTIN_TABLES_VERIFIED else ""
+
+
+class UnverifiedModelTablesWarning(UserWarning):
+    pass
+
+
 class Model:
     """Owns one `mwrt_model*`.  Immutable after creation, safe to share between plans."""
 
     def __init__(self, name):
         lib = _lib.load()
         self.name = name
+        self.verified = BUILTIN_TABLES_VERIFIED
+        if not self.verified and name not in _warned and not os.environ.get("MWRT_QUIET"):
+            _warned.add(name)
+            warnings.warn(provenance(name), UnverifiedModelTablesWarning, stacklevel=3)
         h = C.c_void_p()
         _lib.check(lib.mwrt_model_create(name.encode(), C.byref(h)), "init_absmdl('%s')" % name)
         self._h = h
@@ -73,6 +97,7 @@ class Model:
         d, keep = _pack(desc)
         self = cls.__new__(cls)
         self.name = desc.get("name", "custom")
+        self.verified = bool(desc.get("verified", False))
         h = C.c_void_p()
         _lib.check(lib.mwrt_model_create_custom(C.byref(d), C.byref(h)), "model_create_custom")
         del keep

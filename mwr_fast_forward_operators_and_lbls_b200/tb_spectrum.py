@@ -75,29 +75,44 @@ class TbCloudRTE:
         if self.denice.shape != self.z.shape or self.denliq.shape != self.z.shape:
             raise ValueError("denice/denliq must have one value per level")
 
+    def _cloud_levels(self):
+        """Level indices of the first cloud layer's base and top (`cldh` heights are matched to the
+        nearest level, heights taken above the antenna like upstream's `z -= z[0]`)."""
+        if not (self.cloudy and self.cldh.shape[1] > 0) or self.satellite:
+            return None
+        zrel = self.z - self.z[0]
+        base, top = self.cldh[:, 0] - self.z[0]
+        return int(np.argmin(np.abs(zrel - base))), int(np.argmin(np.abs(zrel - top)))
+
     def execute(self, only_bt=True):
         if self._model is None:
             raise ValueError("init_absmdl() must be called before execute()")
         dl = di = None
         if self.cloudy:
             dl, di = _dev64(self.denliq[None]), _dev64(self.denice[None])
+        cld = self._cloud_levels()
+        names = FIELDS + (("tmrcld",) if cld is not None else ())
         # one device buffer for all fields -> one device-to-host copy
-        buf = torch.empty((len(FIELDS), 1, self.nf, self.nang), dtype=torch.float64, device="cuda")
-        out = {f: buf[i] for i, f in enumerate(FIELDS)}
+        buf = torch.empty((len(names), 1, self.nf, self.nang), dtype=torch.float64, device="cuda")
+        out = {f: buf[i] for i, f in enumerate(names)}
+        kw = {}
+        if cld is not None:
+            kw = dict(cld_ibase=torch.tensor([cld[0]], dtype=torch.int32, device="cuda"),
+                      cld_itop=torch.tensor([cld[1]], dtype=torch.int32, device="cuda"))
         with _PLAN_LOCK:                  # cached plans are shared; a plan runs one call at a time
             plan = _cached_plan(self._model, self.nl, self.frq, self.angles, self.ray_tracing,
                                 self.satellite, self.cloudy, self.emissivity)
             res = plan.forward(_dev64(self.z[None]), _dev64(self.p[None]), _dev64(self.tk[None]),
-                               _dev64(self.rh[None]), dl, di, out=out)
+                               _dev64(self.rh[None]), dl, di, fields=names, out=out, **kw)
             host = buf.cpu().numpy()      # synchronises the stream
             status = int(res["status"][0].item())
         if status & _lib.ST_NEG_ABS:
             raise ValueError("Error encountered in exponential_integration")  # upstream's message
         cols = {}
         for c in COLUMNS:
-            if c in FIELDS:
-                cols[c] = host[FIELDS.index(c), 0].T.reshape(self.nf * self.nang)  # angle-major
-            else:
+            if c in names:
+                cols[c] = host[names.index(c), 0].T.reshape(self.nf * self.nang)  # angle-major
+            else:      # tmrcld without a cloud layer: 0, as upstream
                 cols[c] = np.zeros(self.nf * self.nang)
         df = pd.DataFrame(cols)
         df["angle"] = np.repeat(self.angles, self.nf)

@@ -96,6 +96,20 @@ def run(tasks, levels, model, steps=1, warmup=0, cores=None, seed=1234):
                 tb_per_step=ntb, checksum=float(np.sum(res)))
 
 
+def parity_sample(path, nprof, levels, model, seed=4321):
+    """The checker half of bench.py's cpu_baseline leg: the vectorised oracle on `nprof` synthetic
+    profiles (seeded, so bench.py feeds the SAME profiles to the GPU), all channels and elevations;
+    written to `path` (.npz) for bench.py to take max |dTB| against, outside any timed region."""
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    from oracle import pyrtlib_vec
+    synth = _load_synth()
+    d = synth.synth_profiles(nprof, levels, seed=seed)
+    ref = pyrtlib_vec.simulate(d["z"], d["p"], d["t"], d["rh"], synth.HATPRO_FRQ, synth.HATPRO_ELEV, model)
+    np.savez(path, seed=seed, nprof=nprof, levels=levels, model=model,
+             **{k: ref[k] for k in ("tbtotal", "tbatm", "tmr", "tauwet", "taudry")})
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tasks", type=int, default=0, help="execute() calls per step (0: calibrate)")
@@ -105,7 +119,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=0)
     ap.add_argument("--cores", type=int, default=0)
     ap.add_argument("--budget-s", type=float, default=15.0, help="target CPU wall time for all steps")
+    ap.add_argument("--parity-out", default="", help="also write the oracle's outputs for a seeded sample (.npz)")
+    ap.add_argument("--parity-profiles", type=int, default=256)
     a = ap.parse_args()
+    if a.parity_out:
+        parity_sample(a.parity_out, a.parity_profiles, a.levels, a.model)
     cores = a.cores or os.cpu_count() or 1
     tasks = a.tasks
     if tasks <= 0:

@@ -127,7 +127,11 @@ def test_hot_kernel_resource_budget(built_lib):
                       r"stores, (\d+) bytes spill loads\n.*?Used (\d+) registers" % re.escape(mangled_prefix), text)
         assert m, "kernel %s not found in build.log" % mangled_prefix
         return dict(spill_st=int(m.group(3)), spill_ld=int(m.group(4)), regs=int(m.group(5)))
-    k1 = usage("_ZN4mwrt12k_absorptionILi14EEE")
+    k1 = usage("_ZN4mwrt12k_absorptionILi14ELb0EEE")
     assert k1["regs"] <= 128 and k1["spill_st"] <= 128, k1
-    k3 = usage("_ZN4mwrt5k_rteILi10ELb0ELb1ELb0ELb0EEE")
+    k1f = usage("_ZN4mwrt12k_absorptionILi14ELb1EEE")           # fp32 line-shape mode
+    assert k1f["regs"] <= 128 and k1f["spill_st"] <= 160, k1f
+    k3 = usage("_ZN4mwrt5k_rteILi10ELb0ELb1ELb0ELb0ELb0EEE")    # clear sky, plane-parallel
     assert k3["regs"] <= 170 and k3["spill_st"] == 0, k3
+    k3bp = usage("_ZN4mwrt5k_rteILi10ELb1ELb1ELb0ELb0ELb1EEE")  # cloudy + fused band-pass: 384 threads/CTA
+    assert k3bp["regs"] <= 170, k3bp
