@@ -280,7 +280,7 @@ def main():
     import torch
     import torch.distributed as dist
     import mwr_fast_forward_operators_and_lbls_b200 as pkg
-    from mwr_fast_forward_operators_and_lbls_b200 import _lib, roofline
+    from mwr_fast_forward_operators_and_lbls_b200 import _lib, hostbind, roofline
     from mwr_fast_forward_operators_and_lbls_b200.distributed import (CopyEngineGather, FusedGatherForward,
                                                                      PipelinedForward)
     from mwr_fast_forward_operators_and_lbls_b200.forward import _ptr, _stream
@@ -292,6 +292,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    # the host entry point's pinned buffers are first-touched on the GPU's own NUMA node (hostbind.py);
+    # MWRT_NO_BIND=1 keeps the inherited affinity (for the with/without comparison of tools/e2e_diag.py)
+    orig_affinity = os.sched_getaffinity(0)
+    numa = ({"bound": False, "why": "MWRT_NO_BIND"} if os.environ.get("MWRT_NO_BIND")
+            else hostbind.bind_to_gpu_node(local))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N = world
@@ -550,6 +555,7 @@ def main():
     # ---- cpu_baseline leg: the PyRTlib-shaped port timed on the host cores (N=1 only) and the oracle as
     # the CHECKER of this run's GPU results on 256 seeded profiles (outside every timed region)
     cpu, parity = None, None
+    os.sched_setaffinity(0, orig_affinity)      # the CPU arm may use every host core again
     if not args.no_cpu_baseline:
         with tempfile.TemporaryDirectory() as tmp:
             pfile = os.path.join(tmp, "parity.npz")
@@ -584,6 +590,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "api": "Plan.forward_host -> mwrt_plan_forward_host (pinned host buffers)",
+                    "numa": numa,
                     "fields_moved": moved,
                     "note": "all six outputs delivered to host arrays; tauliq (identically 0 in clear sky) "
                             "is filled by the host while the GPU works instead of crossing PCIe",

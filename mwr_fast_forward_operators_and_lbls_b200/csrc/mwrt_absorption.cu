@@ -45,18 +45,6 @@ __device__ __forceinline__ float rcp_f32(float x) {   // MUFU.RCP, ~1 ulp (fp32 
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
-__device__ __forceinline__ double sqrt_f(double x) {  // x > 0, normal
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double h = 0.5 * y, s = x * y;
-  double e = fma(-s, h, 0.5);
-  s = fma(s, e, s);
-  h = fma(h, e, h);
-  e = fma(-s, h, 0.5);
-  s = fma(s, e, s);
-  h = fma(h, e, h);
-  return fma(fma(-s, s, x), h, s);
-}
 __device__ __forceinline__ cplx csqrt_f(cplx z) {  // principal root, z != 0
   const double m = sqrt_f(fma(z.re, z.re, z.im * z.im));
   const double t = sqrt_f(0.5 * (m + fabs(z.re)));
@@ -204,62 +192,22 @@ struct PairHot {   // what the pair loop keeps live: 8 doubles
 };
 
 // The innermost loop of kernel 1: one line PAIR against the FB frequencies of the block (see the
-// derivation above H2OLine).  Written stage by stage over groups of G frequencies with ordered FP64 ops
-// (MWRT_FMA & co., mwrt_common.cuh): left to itself the compiler software-pipelines only two
-// frequencies deep, so a warp sits on the MUFU.RCP64H latency and on back-to-back dependent DFMAs
-// (profiles/r01m: `wait` 2.2 and `short_scoreboard` 0.7 warps per issue); with G chains in flight per
-// warp the G reciprocal seeds are issued together and every later stage finds its operands ready.
-#ifndef MWRT_ABS_GROUP
-#define MWRT_ABS_GROUP 7
-#endif
-template <int FB, int G>
+// derivation above H2OLine).  The compiler software-pipelines it two frequencies deep.  Forcing more
+// chains in flight (stage-by-stage groups of 4 / 7 / 14 frequencies with ordered FP64 ops) was measured
+// on B200 and did NOT help: 0.808 / 0.811 / 0.842 ms against 0.805 ms for config 2 and 8.84 against
+// 8.32 ms at F = 700 (profiles/r02c_variants.txt) -- ptxas re-serialises most of it and the extra live
+// registers cost spills; neither did 5 or 3 CTAs per SM (0.875 / 0.816 ms).
+template <int FB>
 __device__ __forceinline__ void pair_accumulate(double (&acc)[FB], const double2* __restrict__ fsq2,
                                                 const PairHot& h) {
-#if MWRT_ABS_GROUP == 0   // reference form: one frequency after the other, scheduling left to the compiler
 #pragma unroll
   for (int j = 0; j < FB; ++j) {
-    const double u = (j & 1) ? fsq2[j >> 1].y : fsq2[j >> 1].x;
+    const double u = (j & 1) ? fsq2[j >> 1].y : fsq2[j >> 1].x;   // LDS.128: two frequencies per load
     const double va = u - h.c3a, vb = u - h.c3b;
     const double Da = fma(va, va, h.c4a), Db = fma(vb, vb, h.c4b);
     const double na = fma(h.n1a, va, h.n0a), nb = fma(h.n1b, vb, h.n0b);
     const double num = fma(nb, Da, na * Db);
     acc[j] = fma(num, rcp_nr1(Da * Db), acc[j]);
-  }
-  return;
-#endif
-#pragma unroll
-  for (int j0 = 0; j0 < FB; j0 += G) {
-    double va[G], vb[G], Da[G], Db[G], na[G], nb[G], pr[G], r[G];
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      const int j = (j0 + q < FB) ? j0 + q : FB - 1;
-      const double u = (j & 1) ? fsq2[j >> 1].y : fsq2[j >> 1].x;   // LDS.128: two frequencies per load
-      MWRT_ADD(va[q], u, -h.c3a);
-      MWRT_ADD(vb[q], u, -h.c3b);
-    }
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      MWRT_FMA(Da[q], va[q], va[q], h.c4a);
-      MWRT_FMA(Db[q], vb[q], vb[q], h.c4b);
-      MWRT_FMA(na[q], h.n1a, va[q], h.n0a);
-      MWRT_FMA(nb[q], h.n1b, vb[q], h.n0b);
-    }
-#pragma unroll
-    for (int q = 0; q < G; ++q) {
-      MWRT_MUL(pr[q], Da[q], Db[q]);
-      MWRT_MUL(na[q], na[q], Db[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < G; ++q) asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(r[q]) : "d"(pr[q]));
-#pragma unroll
-    for (int q = 0; q < G; ++q) MWRT_FMA(nb[q], nb[q], Da[q], na[q]);     // numerator
-#pragma unroll
-    for (int q = 0; q < G; ++q) MWRT_FMA(pr[q], -pr[q], r[q], 1.0);       // Newton residual
-#pragma unroll
-    for (int q = 0; q < G; ++q) MWRT_FMA(r[q], r[q], pr[q], r[q]);        // rcp_nr1
-#pragma unroll
-    for (int q = 0; q < G; ++q)
-      if (j0 + q < FB) MWRT_FMA(acc[j0 + q], nb[q], r[q], acc[j0 + q]);
   }
 }
 
@@ -449,10 +397,6 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
 
   const long long obase = (pidx * F + f0) * (long long)L + lev;  // + j*L per frequency
   const double2* fsq2 = reinterpret_cast<const double2*>(fsq);   // fsq is 16-byte aligned (even offsets)
-  // frequencies per staged group of the pair loop: a divisor-friendly size near MWRT_ABS_GROUP
-  constexpr int kGroupWish = MWRT_ABS_GROUP > 0 ? MWRT_ABS_GROUP : 1;
-  constexpr int kGroup = (FB % kGroupWish == 0) ? kGroupWish
-                         : (FB % 8 == 0 ? 8 : (FB % 5 == 0 ? 5 : (FB % 4 == 0 ? 4 : kGroupWish)));
   double acc[FB];
   float accf[F32 ? FB : 1];   // fp32 mode: the pair-loop sums of one species (scaled by 2^40); the fp64
                               // `acc` then only collects the corrections
@@ -559,7 +503,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
             }
           } else {
           const PairHot h{ga.c3, ga.c4, ga.n1, ga.n0, gb.c3, gb.c4, gb.n1 * zb, gb.n0 * zb};
-          pair_accumulate<FB, kGroup>(acc, fsq2, h);
+          pair_accumulate<FB>(acc, fsq2, h);
           }
           if (hchk[ia] | hchk[ib]) {   // uniform: almost every pair skips the per-thread tests
             ma = (hchk[ia] && needs_corr(ga, ia, Ra[MWRT_H2O_FL])) ? kSlowCorr : kSlowNone;
@@ -771,7 +715,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
           }
         } else {
         const PairHot h{oa.c3, oa.c4, oa.n1, oa.n0, ob.c3, ob.c4, ob.n1, ob.n0};
-        pair_accumulate<FB, kGroup>(acc, fsq2, h);
+        pair_accumulate<FB>(acc, fsq2, h);
         }
         // rare: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency
         if (!(ochk[k] | ochk[k + 1])) continue;   // uniform, decided per CTA

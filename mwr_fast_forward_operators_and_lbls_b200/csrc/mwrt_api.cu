@@ -907,7 +907,7 @@ int mwrt_cloud_features_f64(int S, int L, const double* p, const double* t, cons
 }
 
 int mwrt_math_selftest_f64(int op, int64_t n, const double* x, double* y, void* stream) {
-  if (n <= 0 || !x || !y || op < 0 || op > MWRT_MATH_RCP_NR1)
+  if (n <= 0 || !x || !y || op < 0 || op > MWRT_MATH_ATAN2_M1X)
     return fail_arg(MWRT_E_ARG, "mwrt_math_selftest_f64: bad argument");
   return math_selftest_launch(op, n, x, y, (cudaStream_t)stream);
 }

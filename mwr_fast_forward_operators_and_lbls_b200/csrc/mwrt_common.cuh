@@ -16,7 +16,7 @@ namespace mwrt {
 constexpr double kPlanckH = 6.6260755e-34;
 constexpr double kBoltzmannK = 1.380658e-23;
 constexpr double kLightC = 299792458.0;
-constexpr double kTCosmic = 2.73;
+constexpr double kTCosmic = 2.736;   // constants('Tcosmicbkg'): 2.736 +/- 0.017 K (Janssen 1993, p. 12)
 constexpr double kEarthRadius = 6370.949;
 constexpr double kRWatVap = 461.5;
 constexpr double kSqrtPi = 1.77245385090551603;
@@ -326,6 +326,21 @@ __device__ __forceinline__ void rcp_nr1_vec(const double (&x)[N], double (&y)[N]
   for (int a = 0; a < N; ++a) MWRT_FMA(e[a], -x[a], r[a], 1.0);
 #pragma unroll
   for (int a = 0; a < N; ++a) MWRT_FMA(y[a], r[a], e[a], r[a]);
+}
+
+// ---- square root without the IEEE slow path -------------------------------------------------------
+// MUFU.RSQ64H seed + two coupled Newton steps + one residual correction (<= 1 ulp) for normal x > 0.
+__device__ __forceinline__ double sqrt_f(double x) {  // x > 0, normal
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double h = 0.5 * y, s = x * y;
+  double e = fma(-s, h, 0.5);
+  s = fma(s, e, s);
+  h = fma(h, e, h);
+  e = fma(-s, h, 0.5);
+  s = fma(s, e, s);
+  h = fma(h, e, h);
+  return fma(fma(-s, s, x), h, s);
 }
 
 // ---- branch-free atan2 ---------------------------------------------------------------------------

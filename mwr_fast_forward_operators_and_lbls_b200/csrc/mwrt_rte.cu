@@ -126,6 +126,7 @@ k_slant_path(const int P, const int L, const int A, const double* __restrict__ z
     }
     const double theta0 = angle * (pi / 180.0);
     const double rs = re + zr[0] + z0;
+    const double irs = 1.0 / rs;
     const double cos0 = cos(theta0), sin0 = sin(theta0);
     const double sina = sin(theta0 * 0.5);
     const double a0 = 2.0 * sina * sina;
@@ -141,23 +142,25 @@ k_slant_path(const int P, const int L, const int A, const double* __restrict__ z
       const double zi = zr[lc], zl = zr[lc - 1];
       const double ni = nn[lc];
       const double r = re + zi + z0, rl = re + zl + z0;
-      const double argdth = zi / rs - (n0 - ni) * cos0 / ni;
-      const double argth = 0.5 * (a0 + argdth) / r;
+      // (divisions and square roots through the MUFU-seeded helpers of mwrt_common.cuh: every operand
+      // here is a normal positive number, no IEEE slow path is needed)
+      const double argdth = zi * irs - (n0 - ni) * cos0 * rcp_fast(ni);
+      const double argth = 0.5 * (a0 + argdth) * rcp_fast(r);
       const bool ok = argth > 0.0;                       // else: ducting
-      const double sint = sqrt(ok ? r * argth : 0.25);   // sin(theta / 2)
-      const double cosal = sqrt(fmax(1.0 - sint * sint, 0.0));   // cos(theta / 2)
+      const double sint = sqrt_f(ok ? r * argth : 0.25); // sin(theta / 2)
+      const double cosal = sqrt_f(fmax(1.0 - sint * sint, 1e-300));   // cos(theta / 2)
       double dtheta, cot;
       if (sint <= sin0) {                                // theta <= 2 theta0
-        const double ch = sqrt(0.5 * (1.0 + cosal));     // cos(theta / 4)
-        const double sh = sint / (2.0 * ch);             // sin(theta / 4)
+        const double ch = sqrt_f(0.5 * (1.0 + cosal));   // cos(theta / 4)
+        const double sh = sint * rcp_fast(2.0 * ch);     // sin(theta / 4)
         const double dendth = 2.0 * (sint + sina) * (ch * c40 - sh * s40);   // .. cos((theta + theta0) / 4)
-        const double sind4 = (0.5 * argdth - zi * argth) / dendth;
+        const double sind4 = div_fast(0.5 * argdth - zi * argth, dendth);
         dtheta = 4.0 * (fabs(sind4) < 0.05 ? asin_small(sind4) : asin(sind4));
         // cot(theta0 + dtheta) from sin(dtheta / 4) by two double-angle steps
-        const double c4 = sqrt(fmax(1.0 - sind4 * sind4, 0.0));
+        const double c4 = sqrt_f(fmax(1.0 - sind4 * sind4, 1e-300));
         const double s2 = 2.0 * sind4 * c4, c2 = 1.0 - 2.0 * sind4 * sind4;
         const double s1 = 2.0 * s2 * c2, c1 = 1.0 - 2.0 * s2 * s2;
-        cot = (cos0 * c1 - sin0 * s1) / (sin0 * c1 + cos0 * s1);
+        cot = div_fast(cos0 * c1 - sin0 * s1, sin0 * c1 + cos0 * s1);
       } else {
         dtheta = 2.0 * asin(sint) - theta0;
         cot = (1.0 - 2.0 * sint * sint) / (2.0 * sint * cosal);
@@ -180,10 +183,10 @@ k_slant_path(const int P, const int L, const int A, const double* __restrict__ z
       const double x = (phi - phil) * 0.5;
       const double shx = fabs(x) < 0.05 ? sin_small(x) : sin(x);
       const double dz = zi - zl;
-      double dsi = sqrt(dz * dz + 4.0 * r * rl * (shx * shx));
+      double dsi = sqrt_f(fmax(dz * dz + 4.0 * r * rl * (shx * shx), 1e-300));
       if (dtau != 0.0) {   // dtaua / (2 sin(dtaua / 2)), dtaua = |dtau|
         const double y = fabs(dtau) * 0.5;
-        dsi = dsi * (y < 0.05 ? y / sin_small(y) : y / sin(y));
+        dsi = dsi * (y < 0.05 ? div_fast(y, sin_small(y)) : y / sin(y));
       }
       const int first = badmask ? __ffs(badmask) - 1 : 32;
       if (ducted || lane >= first) dsi = 0.0;   // the rest of the path stays 0, like upstream

@@ -27,7 +27,9 @@ from . import model_tables
 PLANCK_H = 6.6260755e-34      # J s
 BOLTZMANN_K = 1.380658e-23    # J/K
 LIGHT_C = 299792458.0         # m/s
-T_COSMIC = 2.73               # K
+T_COSMIC = 2.736              # K: constants('Tcosmicbkg'), 2.736 +/- 0.017 K (Janssen, Atmospheric Remote Sensing
+                              # by Microwave Radiometry, p. 12) -- the value of the NOAA/Cimini RTE package
+                              # PyRTlib was ported from; round 1 carried 2.73 (a ~5e-3 K K-band offset)
 EARTH_RADIUS = 6370.949       # km
 R_WATVAP = 461.5              # J/(kg K)
 SQRT_PI = 1.77245385090551603
