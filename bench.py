@@ -207,33 +207,34 @@ def run_config(pkg, cfg, rank, world, reps=3, scale=1.0):
         out["tau_layer"] = torch.empty((P, F, L), dtype=torch.float64, device="cuda")
     full = torch.empty((world * pmax, nf, Fo, A), dtype=torch.float64, device="cuda") if world > 1 else None
 
-    def one_pass():
-        plan.forward(dev["z"], dev["p"], dev["t"], dev["rh"], dev.get("denliq"), dev.get("denice"),
-                     fields=fields, out=out)
-        if world > 1:
-            for i, k in enumerate(fields):
-                stacked[:P, i].copy_(out[k])
-            dist.all_gather_into_tensor(full, stacked)
-    ts = []
+    ts, tc = [], []
     for it in range(1 + reps):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, em, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        one_pass()
+        plan.forward(dev["z"], dev["p"], dev["t"], dev["rh"], dev.get("denliq"), dev.get("denice"),
+                     fields=fields, out=out)
+        em.record()
+        if world > 1:
+            for i, k in enumerate(fields):
+                stacked[:P, i].copy_(out[k])
+            dist.all_gather_into_tensor(full, stacked)
         e1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        t = torch.tensor([e0.elapsed_time(e1), e0.elapsed_time(em)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         if it > 0:
-            ts.append(float(t.item()))
+            ts.append(float(t[0].item()))
+            tc.append(float(t[1].item()))
     ms = float(np.median(ts))
     finite = bool(torch.isfinite(out["tbtotal"]).all().item())
     w = roofline.work(Ptot, L, F, A, cloudy=c["kw"].get("cloudy", False), tau_layers=c["kw"].get("tau_layers", False))
     res = {"config": CONFIG_NAMES[cfg], "profiles_total": Ptot, "profiles_per_rank": P, "levels": L,
            "frequencies": F, "channels_out": Fo, "elevations": A, "n_gpus": world, "ms_per_pass": ms,
+           "ms_kernels_only": float(np.median(tc)), "gathered_gbytes_per_rank": 8.0 * nf * Ptot * Fo * A / 1e9,
            "all_ms": ts, "tb_per_s": Ptot * Fo * A / ms * 1e3, "mono_tb_per_s": Ptot * F * A / ms * 1e3,
            "algorithmic_tflops": w["flops_total"] / ms / 1e9,
            "algorithmic_tflops_per_gpu": w["flops_total"] / ms / 1e9 / world,
@@ -262,11 +263,12 @@ def main():
                          "of that configuration instead (full size, split over the ranks)")
     ap.add_argument("--scale", type=float, default=1.0, help="--config 3/4/5 and extras: fraction of the full size")
     ap.add_argument("--model", default=MODEL)
-    ap.add_argument("--gather", default="ce", choices=["ce", "fused", "nccl"],
-                    help="N>1: 'ce' = every rank pushes its results to each peer with one copy-engine memcpy "
-                         "per peer onto symmetric memory, overlapped with the next step (no collective "
-                         "kernel); 'fused' = kernel 3 stores straight into every rank's buffer over NVLink "
-                         "(multicast / peer stores); 'nccl' = all_gather_into_tensor overlapped with the next step")
+    ap.add_argument("--gather", default="push", choices=["push", "ce", "fused", "nccl"],
+                    help="N>1: 'push' = a small kernel stores each rank's results to the NVLink multicast "
+                         "address of a symmetric buffer while the next step computes (per-peer stores or copy "
+                         "engines where multicast is missing); 'ce' = one copy-engine memcpy per peer; 'fused' = "
+                         "kernel 3 itself stores to every rank's buffer; 'nccl' = all_gather_into_tensor "
+                         "overlapped with the next step")
     ap.add_argument("--split", type=int, default=1,
                     help="mwrt_plan_set_split: pieces of the device-entry batch (kernel 3 of piece c on a side "
                          "stream while kernel 1 of piece c+1 runs)")
@@ -281,8 +283,8 @@ def main():
     import torch.distributed as dist
     import mwr_fast_forward_operators_and_lbls_b200 as pkg
     from mwr_fast_forward_operators_and_lbls_b200 import _lib, hostbind, roofline
-    from mwr_fast_forward_operators_and_lbls_b200.distributed import (CopyEngineGather, FusedGatherForward,
-                                                                     PipelinedForward)
+    from mwr_fast_forward_operators_and_lbls_b200.distributed import (FusedGatherForward, PipelinedForward,
+                                                                     PushGather)
     from mwr_fast_forward_operators_and_lbls_b200.forward import _ptr, _stream
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -333,17 +335,20 @@ def main():
     ovl = None
     gather_desc = "none"
     if N > 1:
-        if args.gather == "ce":
+        if args.gather in ("push", "ce"):
             try:
-                ovl = CopyEngineGather(plan, P, fields)
-                gather_desc = ("copy engines: every rank pushes its %d fields (%s; tauliq is identically zero in "
-                               "clear sky and is rebuilt from the gathered status words) to each of the %d peers "
-                               "with ONE cudaMemcpyAsync per peer onto symmetric memory, on side streams, while "
-                               "the next step computes; one symmetric-memory barrier per step; no collective "
-                               "kernel" % (len(ovl.moved), ",".join(ovl.moved), N - 1))
+                ovl = PushGather(plan, P, fields, transport="auto" if args.gather == "push" else "ce")
+                how = {"multicast": "a %d-CTA kernel stores the slot to the buffer's NVLink multicast address "
+                                    "(multimem.st; NVSwitch replicates it to all ranks, a rank sends once)" % ovl.nblocks,
+                       "peers": "a %d-CTA kernel stores the slot to every peer-mapped copy" % ovl.nblocks,
+                       "ce": "one cudaMemcpyAsync per peer on side streams (copy engines)"}[ovl.transport]
+                gather_desc = ("push gather: kernel 3 writes its %d fields (%s; tauliq is identically zero in clear "
+                               "sky and is rebuilt from the gathered status words) into the rank's slot of a "
+                               "symmetric buffer; %s while the next step computes; one symmetric-memory barrier "
+                               "per step; no collective call" % (len(ovl.moved), ",".join(ovl.moved), how))
             except Exception as exc:          # symmetric memory not available: plain NCCL
                 if rank == 0:
-                    print("copy-engine gather unavailable (%r); using NCCL" % (exc,), file=sys.stderr)
+                    print("push gather unavailable (%r); using NCCL" % (exc,), file=sys.stderr)
                 ovl = None
         elif args.gather == "fused":
             try:
@@ -538,6 +543,29 @@ def main():
             "max_abs_dtb_vs_fp64_path_K": dtb, "max_rel_dtau_vs_fp64_path": dtau, "gate_K": 0.01,
             "timing": "one CUDA-event pair around %d steps, L2 flush inside" % n32}
         del plan32, out32
+        # the one-line import swap: the reference's own call pattern, one
+        # TbCloudRTE object per (profile, elevation) with ONE angle, host arrays in, DataFrame out
+        if rank == 0:
+            prof = [d[k][0] for k in keys]
+
+            def one_execute():
+                rte = pkg.TbCloudRTE(prof[0], prof[1], prof[2], prof[3], frq, np.array([19.2]))
+                rte.init_absmdl(args.model)
+                rte.satellite = False
+                return rte.execute()["tbtotal"].values
+            for _ in range(5):
+                one_execute()
+            t0 = time.perf_counter()
+            ncall = 200
+            for _ in range(ncall):
+                tb1 = one_execute()
+            dt = (time.perf_counter() - t0) / ncall
+            extra["class_api"] = {
+                "what": "TbCloudRTE(z,p,t,rh,frq,[angle]); init_absmdl; satellite=False; execute() -- the "
+                        "reference's per-call pattern (PyRTlib_processing.py:123-127) through the drop-in class, "
+                        "wall clock per call incl. H2D, two kernels, D2H and the DataFrame",
+                "ms_per_execute": dt * 1e3, "tb_per_s": len(frq) / dt, "calls": ncall,
+                "finite": bool(np.isfinite(tb1).all())}
         cfgs = []
         for cfg in (3, 5, 4):
             try:

@@ -191,6 +191,14 @@ int mwrt_plan_set_output_fanout(mwrt_plan* plan, int mode, int npeer, const int6
  * runs a collective kernel.  (One plain cudaMemcpyAsync per copy: the batched-memcpy entry points of
  * CUDA 12.8+ are deliberately not used.) */
 int mwrt_push_async(void* dst, const void* src, int64_t bytes, void* stream);
+/* Multi-GPU gather as a small PUSH KERNEL over NVLink (the default of bench.py --gpus N): `nblocks` CTAs
+ * (<= 0: 8) copy `bytes` (multiple of 16, 16-byte aligned) from `src` on this GPU
+ *   - to `mc_dst`, the NVLink MULTICAST address of the same offset of a symmetric buffer: one
+ *     `multimem.st` per 16 bytes, NVSwitch replicates it into every rank's copy (a rank sends ONCE); or,
+ *   - when mc_dst is NULL, to each of the `npeer` peer-mapped addresses in peer_dst (one store per peer).
+ * Asynchronous on `stream`; the caller orders the ranks afterwards (symmetric-memory barrier). */
+int mwrt_push_kernel(const void* src, int64_t bytes, void* mc_dst, const int64_t* peer_dst, int npeer,
+                     int nblocks, void* stream);
 /* optional band-pass: C channels x S sub-frequencies (C*S == F), host weights (C,S) or NULL = 1/S.
  * Outputs of the forward calls become (P,C,A).  The average is taken INSIDE kernel 3 (fixed summation
  * order, bit-identical to mwrt_bandpass_f64 on the monochromatic fields) whenever a channel's S

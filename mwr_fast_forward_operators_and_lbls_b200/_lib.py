@@ -73,6 +73,8 @@ SYMBOLS = {
     "mwrt_plan_forward_host": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Profiles),
                                          C.POINTER(Outputs)]),
     "mwrt_push_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "mwrt_push_kernel": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_int,
+                                   C.c_void_p]),
     "mwrt_plan_set_output_fanout": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
     "mwrt_stats_f64": (C.c_int, [C.c_int, C.c_int64] + [C.c_void_p] * 7),
     "mwrt_thin_mean_f64": (C.c_int, [C.c_int] * 3 + [C.c_void_p] * 12),

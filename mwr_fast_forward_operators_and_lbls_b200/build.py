@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("MWRT_LIB_OUT") or os.path.join(HERE, "libmwrt.so")  # override: experiments only
 SOURCES = ["mwrt_api.cu", "mwrt_absorption.cu", "mwrt_rte.cu", "mwrt_rte_fanout.cu", "mwrt_post.cu",
-           "mwrt_peak.cu"]
+           "mwrt_peak.cu", "mwrt_push.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v", "--fmad=true"]
 

@@ -219,7 +219,8 @@ constexpr int kSlowNone = 0, kSlowCorr = 1, kSlowExact = 2;
 __host__ __device__ inline int abs_smem_doubles(int nh, int no, int FB) {
   const int nop = (no + 1) & ~1;
   // hrow, orow, fblk, fsq, dfm, dfp, dminh, dmino, then ints: hcls[nh], hord[nh], cnt[2], hchk[nh], ochk[nop]
-  return nh * kHS + nop * kOS + 2 * FB + 2 * nh * FB + nh + nop + (3 * nh + nop + 2 + 1) / 2 + 1;
+  const int n = nh * kHS + nop * kOS + 2 * FB + 2 * nh * FB + nh + nop + (3 * nh + nop + 2 + 1) / 2 + 1;
+  return (n + 1) & ~1;   // even: what follows (the fp32 tables) stays 16-byte aligned
 }
 
 #ifndef MWRT_ABS_MINB
@@ -238,6 +239,30 @@ constexpr double kF32Scale = 1099511627776.0, kF32Unscale = 1.0 / 1099511627776.
 struct PairHotF {
   float ba, c4a, n1a, n0a, bb, c4b, n1b, n0b;
 };
+// fp32 form of the pair loop: the detunings (f^2 - f_line^2) come four at a time from the CTA's fp32
+// tables (LDS.128), everything else lives in registers
+template <int FB>
+__device__ __forceinline__ void pair_accumulate_f32(float (&accf)[FB], const float* __restrict__ Aa,
+                                                    const float* __restrict__ Ab, const PairHotF& h) {
+  const float4* Aa4 = reinterpret_cast<const float4*>(Aa);
+  const float4* Ab4 = reinterpret_cast<const float4*>(Ab);
+#pragma unroll
+  for (int j4 = 0; j4 < FB; j4 += 4) {
+    const float4 qa = Aa4[j4 >> 2], qb = Ab4[j4 >> 2];
+    const float ua[4] = {qa.x, qa.y, qa.z, qa.w}, ub[4] = {qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (j4 + q < FB) {
+        const float va = ua[q] - h.ba, vb = ub[q] - h.bb;
+        const float Da = fmaf(va, va, h.c4a), Db = fmaf(vb, vb, h.c4b);
+        const float na = fmaf(h.n1a, va, h.n0a), nb = fmaf(h.n1b, vb, h.n0b);
+        const float num = fmaf(nb, Da, na * Db);
+        accf[j4 + q] = fmaf(num, rcp_f32(Da * Db), accf[j4 + q]);
+      }
+    }
+  }
+}
+
 template <int FB, bool F32>
 __global__ void __launch_bounds__(kAbsThreads, FB > 16 ? 3 : MWRT_ABS_MINB)
 k_absorption(const ModelDev m, const long long npts, const int L, const int F, const int nfb,
@@ -261,9 +286,11 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
   int* cnt = hord + nh;                   // [0] all-in lines, [1] lines that contribute at all
   int* hchk = cnt + 2;                    // nh: can this line need a correction in this block at all?
   int* ochk = hchk + nh;                  // nop: same for the O2 lines
-  // fp32 line-shape mode: (f_j^2 - f_line^2) rounded to fp32, nh x FB then nop x FB
+  // fp32 line-shape mode: (f_j^2 - f_line^2) rounded to fp32, nh rows then nop rows of FBP floats
+  // (rows padded to a multiple of four so that one LDS.128 brings four frequencies)
+  constexpr int FBP = (FB + 3) & ~3;
   float* a32h = reinterpret_cast<float*>(smem + abs_smem_doubles(nh, no, FB));
-  float* a32o = a32h + nh * FB;
+  float* a32o = a32h + nh * FBP;
   __shared__ double etab[kExpTabN];             // exp_tb / log_tb tables (mwrt_common.cuh)
   __shared__ __align__(16) double ltab[128];
   exp_tab_stage(etab);
@@ -305,12 +332,14 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
       dfp[i] = f + fl;
     }
     if (F32) {
-      for (int i = threadIdx.x; i < nh * FB; i += blockDim.x) {
-        const double fl = hrow[(i / FB) * kHS + MWRT_H2O_FL], f = fblk[i % FB];
+      for (int i = threadIdx.x; i < nh * FBP; i += blockDim.x) {
+        const int jj = i % FBP;
+        const double fl = hrow[(i / FBP) * kHS + MWRT_H2O_FL], f = fblk[jj < FB ? jj : FB - 1];
         a32h[i] = (float)((f - fl) * (f + fl));
       }
-      for (int i = threadIdx.x; i < nop * FB; i += blockDim.x) {
-        const double fk = orow[(i / FB) * kOS + MWRT_O2_F], f = fblk[i % FB];
+      for (int i = threadIdx.x; i < nop * FBP; i += blockDim.x) {
+        const int jj = i % FBP;
+        const double fk = orow[(i / FBP) * kOS + MWRT_O2_F], f = fblk[jj < FB ? jj : FB - 1];
         a32o[i] = (float)((f - fk) * (f + fk));
       }
     }
@@ -491,16 +520,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
             const PairHotF h{(float)ga.b32, (float)ga.c4, (float)(ga.n1 * kF32Scale), (float)(ga.n0 * kF32Scale),
                              (float)gb.b32, (float)gb.c4, (float)(gb.n1 * (zb * kF32Scale)),
                              (float)(gb.n0 * (zb * kF32Scale))};
-            const float* Aa = a32h + ia * FB;
-            const float* Ab = a32h + ib * FB;
-#pragma unroll
-            for (int j = 0; j < FB; ++j) {
-              const float va = Aa[j] - h.ba, vb = Ab[j] - h.bb;
-              const float Da = fmaf(va, va, h.c4a), Db = fmaf(vb, vb, h.c4b);
-              const float na = fmaf(h.n1a, va, h.n0a), nb = fmaf(h.n1b, vb, h.n0b);
-              const float num = fmaf(nb, Da, na * Db);
-              accf[j] = fmaf(num, rcp_f32(Da * Db), accf[j]);
-            }
+            pair_accumulate_f32<FB>(accf, a32h + ia * FBP, a32h + ib * FBP, h);
           } else {
           const PairHot h{ga.c3, ga.c4, ga.n1, ga.n0, gb.c3, gb.c4, gb.n1 * zb, gb.n0 * zb};
           pair_accumulate<FB>(acc, fsq2, h);
@@ -703,16 +723,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
         if constexpr (F32) {
           const PairHotF h{(float)oa.b32, (float)oa.c4, (float)(oa.n1 * kF32Scale), (float)(oa.n0 * kF32Scale),
                            (float)ob.b32, (float)ob.c4, (float)(ob.n1 * kF32Scale), (float)(ob.n0 * kF32Scale)};
-          const float* Aa = a32o + k * FB;
-          const float* Ab = a32o + (k + 1) * FB;
-#pragma unroll
-          for (int j = 0; j < FB; ++j) {
-            const float va = Aa[j] - h.ba, vb = Ab[j] - h.bb;
-            const float Da = fmaf(va, va, h.c4a), Db = fmaf(vb, vb, h.c4b);
-            const float na = fmaf(h.n1a, va, h.n0a), nb = fmaf(h.n1b, vb, h.n0b);
-            const float num = fmaf(nb, Da, na * Db);
-            accf[j] = fmaf(num, rcp_f32(Da * Db), accf[j]);
-          }
+          pair_accumulate_f32<FB>(accf, a32o + k * FBP, a32o + (k + 1) * FBP, h);
         } else {
         const PairHot h{oa.c3, oa.c4, oa.n1, oa.n0, ob.c3, ob.c4, ob.n1, ob.n0};
         pair_accumulate<FB>(acc, fsq2, h);
@@ -793,7 +804,7 @@ static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, c
   const unsigned grid = (unsigned)(items < 0x7fffffffLL ? items : 0x7fffffffLL);
   const int nop = (m.n_o2 + 1) & ~1;
   size_t smem = sizeof(double) * (size_t)abs_smem_doubles(m.n_h2o, m.n_o2, FB) +
-                (F32 ? sizeof(float) * (size_t)(m.n_h2o + nop) * FB : 0);
+                (F32 ? sizeof(float) * (size_t)(m.n_h2o + nop) * ((FB + 3) & ~3) : 0);
   if (smem > 48 * 1024) {
     static bool once = [] {
       return cudaFuncSetAttribute(k_absorption<FB, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,

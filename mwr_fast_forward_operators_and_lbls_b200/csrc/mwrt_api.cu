@@ -44,6 +44,8 @@ int slant_path_launch(int P, int L, int A, const double* z, const double* p, con
                       cudaStream_t st);
 int bandpass_launch(int P, int C, int S, int A, const double* in, const double* w, double* out,
                     const Fanout& fo, cudaStream_t st);
+int push_launch(const void* src, long long bytes, void* mc_dst, const long long* peer_dst, int npeer,
+                int nblocks, cudaStream_t st);
 int dfma_peak(double* flops, double* mhz);
 int stats_launch(int T, long long M, const double* values, const double* refs, double* bias,
                  double* sd, double* rmse, double* nvalid, cudaStream_t st);
@@ -470,6 +472,14 @@ int mwrt_push_async(void* dst, const void* src, int64_t bytes, void* stream) {
   if (!dst || !src || bytes <= 0) return fail_arg(MWRT_E_ARG, "mwrt_push_async: bad argument");
   MWRT_CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return 0;
+}
+
+int mwrt_push_kernel(const void* src, int64_t bytes, void* mc_dst, const int64_t* peer_dst, int npeer,
+                     int nblocks, void* stream) {
+  if (!src || bytes <= 0 || (!mc_dst && !peer_dst)) return fail_arg(MWRT_E_ARG, "mwrt_push_kernel: bad argument");
+  static_assert(sizeof(long long) == sizeof(int64_t), "peer addresses are passed as 64-bit integers");
+  return push_launch(src, (long long)bytes, mc_dst, reinterpret_cast<const long long*>(peer_dst), npeer, nblocks,
+                     (cudaStream_t)stream);
 }
 
 int mwrt_plan_set_split(mwrt_plan* pl, int pieces) {

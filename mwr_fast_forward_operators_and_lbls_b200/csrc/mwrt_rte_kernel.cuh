@@ -263,14 +263,6 @@ k_rte(const RteArgs g, const Fanout fo) {
   lvA = lvB;
   lvB = load(L > 2 ? lev0 + 2 * dir : lev0 + dir);
 
-  // ray-traced path: slant path lengths of the layer the first step integrates
-  double dsc[PLANE ? 1 : NA];
-  if (!PLANE) {
-    const int j1 = FROM_SAT ? lev0 : lev0 + 1;     // layer index of step 1 (upper level of the layer)
-#pragma unroll
-    for (int a = 0; a < NA; ++a) dsc[a] = (a0 + a < A) ? dsp[(long long)a * L + j1] : 0.0;
-  }
-
   // one step: the NA-angle stage of the current layer + the scalars of the next one
   auto step_body = [&](auto generic, const int step) {
     const int clev = lev0 + step * dir;          // level reached in this step
@@ -306,16 +298,11 @@ k_rte(const RteArgs g, const Fanout fo) {
     } else {
       // per-angle sums: wet (+ liquid, ice) and the total; the dry sum is total - the others at the end
       // (one subtraction per output instead of NA fused multiply-adds per layer and NA live registers)
-      // the NEXT layer's path lengths are requested now (NA broadcast loads per warp: their latency
-      // was the top stall of this variant, profiles/r02c_prof_raytracing.txt) and used one step later
-      const int jn = (step + 1 < L) ? j + dir : j;
-      double dsn[NA];
-#pragma unroll
-      for (int a = 0; a < NA; ++a) dsn[a] = (a0 + a < A) ? dsp[(long long)a * L + jn] : 0.0;
+      // (prefetching the next layer's path lengths one step ahead was measured 7 % SLOWER: 20 more live
+      // registers in a kernel that already sits at 244)
 #pragma unroll
       for (int a = 0; a < NA; ++a) {
-        const double dsa = dsc[a];
-        dsc[a] = dsn[a];
+        const double dsa = (a0 + a < A) ? dsp[(long long)a * L + j] : 0.0;
         sw[a] = fma(xw, dsa, sw[a]);
         if (CLOUDY) { sl[a] = fma(xl, dsa, sl[a]); si[a] = fma(xi, dsa, si[a]); }
         tau[a] = xtot * dsa;

@@ -165,27 +165,40 @@ class PipelinedForward:
         return self.gathered[slot][:, i].reshape(self.world * self.P_local, self.plan.Fo, self.plan.A)
 
 
-class CopyEngineGather:
-    """The gather on the COPY ENGINES: every rank pushes its finished fields straight into the gathered
-    buffer of each peer with ONE asynchronous device-to-device copy per peer (`mwrt_push_async` =
-    cudaMemcpyAsync onto peer-mapped symmetric memory, one side stream per peer), while the next batch
-    is being computed.  No collective kernel runs, so nothing takes SMs from the two FP64-bound kernels
-    (an NCCL all-gather occupies 16+ CTAs for the whole transfer); a symmetric-memory barrier per step,
-    on the side stream, tells every rank that all pushes of the step have landed.
+class PushGather:
+    """The gather as a PUSH of each rank's finished fields into the gathered buffer of every peer,
+    overlapped with the next batch's kernels -- no collective call, nothing but a barrier to wait for.
+
+    Kernel 3 writes its results directly into this rank's slot of a symmetric buffer
+    (`torch.distributed._symmetric_memory`); the slot then travels by one of three transports:
+
+      "multicast"  `mwrt_push_kernel`: a handful of CTAs store the slot to the buffer's NVLink MULTICAST
+                   address (`multimem.st`), NVSwitch replicates every store into all ranks' copies -- a
+                   rank sends its 56 MB ONCE per step.  Default beyond 4 GPUs.
+      "peers"      the same kernel with one plain store per peer-mapped copy (no multicast support).
+      "ce"         one cudaMemcpyAsync per peer (`mwrt_push_async`) on per-peer side streams: the copy
+                   engines.  Free at 2-4 GPUs, but seven concurrent peer copies reach only ~210 GB/s per
+                   GPU on 8 x B200 (profiles/r02e_check_ce_gather_n8.log: 1.87 ms per step against 1.34
+                   for NCCL and 1.14 of kernels).  Default up to 4 GPUs.
 
     Only what carries information travels: in clear sky `tauliq` / `tauice` are identically zero (NaN
     for flagged profiles) and are rebuilt from the gathered status words by `field()`.
 
-    Kernel 3 writes its results directly into this rank's slot of the symmetric buffer, so there is no
-    local staging copy.  Results of step s: `gathered[s % 2]`, laid out (world, nfield, P_local, F, A)
-    on every rank (double-buffered); `status_g[s % 2]` is (world, P_local).
+    Results of step s: `gathered[s % 2]`, laid out (world, nfield, P_local, F, A) on every rank
+    (double-buffered); `status_g[s % 2]` is (world, P_pad).  A symmetric-memory barrier per step, on
+    the side stream, tells every rank that all pushes of the step have landed.
 
-    Ordering: the pushes of step s+2 overwrite the peers' copy of buffer s % 2, so they wait for the
-    barrier of step s+1 -- every rank arrives there only after the consumers of its step-s results
-    were queued ahead of its step-s+1 kernels.
+    Contract for consumers: the results of step s stay valid in `gathered[s % 2]` until `run()` is
+    called for step s+2 -- consume (or copy) them on a CUDA stream that the CALLING stream of that
+    `run()` is ordered after, typically the calling stream itself.  Mechanism: peers write into this
+    rank's memory without its participation, so every `run()` starts with an ENTRY barrier (queued on
+    the side stream behind an event recorded on the calling stream); the pushes into buffer b wait
+    for it, i.e. until every rank's stream has passed the consumers it queued for what buffer b held.
+    In steady state the entry barrier completes long before the step's kernels do and costs nothing.
     """
 
-    def __init__(self, plan, P_local, fields, group=None):
+    def __init__(self, plan, P_local, fields, group=None, transport="auto", nblocks=0):
+        import os
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self._lib = _lib
@@ -194,6 +207,7 @@ class CopyEngineGather:
         self.group = group if group is not None else dist.group.WORLD
         self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
         self.P_local = int(P_local)
+        self.P_pad = (self.P_local + 3) & ~3          # status rows padded to 16 bytes
         F, A = plan.Fo, plan.A
         zero = () if plan.cloudy else ("tauliq", "tauice")
         self.moved = tuple(f for f in self.fields if f not in zero)
@@ -204,53 +218,102 @@ class CopyEngineGather:
         shape = (self.world, nf, self.P_local, F, A)
         self.gathered = [symm_mem.empty(shape, dtype=torch.float64, device=dev) for _ in range(2)]
         self.hdl = [symm_mem.rendezvous(g, self.group) for g in self.gathered]
-        self.status_g = [symm_mem.empty((self.world, self.P_local), dtype=torch.int32, device=dev) for _ in range(2)]
+        self.status_g = [symm_mem.empty((self.world, self.P_pad), dtype=torch.int32, device=dev) for _ in range(2)]
         self.hdl_st = [symm_mem.rendezvous(g, self.group) for g in self.status_g]
+        for g in self.status_g:
+            g.zero_()
         self.rank_bytes = nf * self.P_local * F * A * 8
-        self.st_bytes = self.P_local * 4
-        # addresses of THIS rank's slot inside every peer's buffers, as mapped into this process
+        self.st_bytes = self.P_pad * 4
+        mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.hdl + self.hdl_st]
+        if transport == "auto":
+            # measured on B200: up to 4 GPUs the copy engines deliver the slots for
+            # free (no SM shared with the kernels); at 8 GPUs seven concurrent peer copies are too slow
+            # and the multicast kernel, which sends every byte once, wins by 0.5 ms per step
+            transport = "multicast" if (self.world > 4 and all(mc) and self.rank_bytes % 16 == 0) else "ce"
+        if transport == "multicast" and not all(mc):
+            raise RuntimeError("NVLink multicast is not available for this group")
+        if transport in ("multicast", "peers") and self.rank_bytes % 16:
+            raise RuntimeError("the push kernel moves 16-byte words; a rank's slot has %d bytes" % self.rank_bytes)
+        self.transport = transport
+        self.nblocks = int(nblocks or os.environ.get("MWRT_PUSH_BLOCKS", 0) or 8)
+        # addresses of THIS rank's slot: inside every peer's buffers as mapped into this process, and
+        # inside the multicast window
         self.peers = [q for q in range(self.world) if q != self.rank]
         self.dst = [{q: int(self.hdl[b].buffer_ptrs[q]) + self.rank * self.rank_bytes for q in self.peers}
                     for b in range(2)]
         self.dst_st = [{q: int(self.hdl_st[b].buffer_ptrs[q]) + self.rank * self.st_bytes for q in self.peers}
                        for b in range(2)]
-        self.push = {q: torch.cuda.Stream() for q in self.peers}
-        self.comm = torch.cuda.Stream()
+        self.mc = [mc[b] + self.rank * self.rank_bytes for b in range(2)]
+        self.mc_st = [mc[2 + b] + self.rank * self.st_bytes for b in range(2)]
+        if transport == "ce":
+            self.push = {q: torch.cuda.Stream() for q in self.peers}
+        else:
+            self.push = {None: torch.cuda.Stream(priority=-1)}     # one high-priority stream for the kernel
+        self.comm = torch.cuda.Stream(priority=-1)
         self.computed = [torch.cuda.Event() for _ in range(2)]
-        self.pushed = [{q: torch.cuda.Event() for q in self.peers} for _ in range(2)]
+        self.pushed = [{q: torch.cuda.Event() for q in self.push} for _ in range(2)]
         self.landed = [torch.cuda.Event() for _ in range(2)]     # barrier of the step using buffer b passed
+        self.entered = [torch.cuda.Event() for _ in range(2)]    # calling stream reached run() for buffer b
+        self.free = [torch.cuda.Event() for _ in range(2)]       # ... on EVERY rank: buffer b may be overwritten
         self.step = 0
+
+    def _push_slot(self, b, src, src_st):
+        chk, lib = self._lib.check, self.lib
+        if self.transport == "ce":
+            for q in self.peers:
+                st = self.push[q]
+                h = C.c_void_p(st.cuda_stream)
+                chk(lib.mwrt_push_async(C.c_void_p(self.dst[b][q]), C.c_void_p(src), self.rank_bytes, h), "push_async")
+                chk(lib.mwrt_push_async(C.c_void_p(self.dst_st[b][q]), C.c_void_p(src_st), self.st_bytes, h),
+                    "push_async")
+            return
+        h = C.c_void_p(self.push[None].cuda_stream)
+        if self.transport == "multicast":
+            chk(lib.mwrt_push_kernel(C.c_void_p(src), self.rank_bytes, C.c_void_p(self.mc[b]), None, 0,
+                                     self.nblocks, h), "push_kernel")
+            chk(lib.mwrt_push_kernel(C.c_void_p(src_st), self.st_bytes, C.c_void_p(self.mc_st[b]), None, 0, 1, h),
+                "push_kernel")
+        else:
+            n = len(self.peers)
+            arr = (C.c_int64 * n)(*[self.dst[b][q] for q in self.peers])
+            chk(lib.mwrt_push_kernel(C.c_void_p(src), self.rank_bytes, None, arr, n, self.nblocks, h), "push_kernel")
+            arr = (C.c_int64 * n)(*[self.dst_st[b][q] for q in self.peers])
+            chk(lib.mwrt_push_kernel(C.c_void_p(src_st), self.st_bytes, None, arr, n, 1, h), "push_kernel")
 
     def run(self, z, p, t, rh, denliq=None, denice=None):
         b = self.step % 2
         main = torch.cuda.current_stream()
+        # entry barrier: every rank's calling stream is past the consumers of what buffer b held
+        self.entered[b].record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.entered[b])
+            self.hdl_st[b].barrier(channel=b)
+            self.free[b].record(self.comm)
         if self.step >= 2:
             main.wait_event(self.landed[b])       # my pushes out of slot b (two steps ago) are complete
         own = self.gathered[b][self.rank]         # (nf, P_local, F, A): kernel 3 writes here directly
         out = {k: own[i] for i, k in enumerate(self.moved)}
-        out["status"] = self.status_g[b][self.rank]
+        out["status"] = self.status_g[b][self.rank][:self.P_local]
         self.plan.forward(z, p, t, rh, denliq, denice, fields=self.moved, out=out)
         self.computed[b].record(main)
-        src, src_st = own.data_ptr(), self.status_g[b][self.rank].data_ptr()
-        for q in self.peers:
-            st = self.push[q]
+        for st in self.push.values():
             st.wait_event(self.computed[b])
-            if self.step >= 1:
-                st.wait_event(self.landed[1 - b])  # peers are done with what buffer b held two steps ago
-            h = C.c_void_p(st.cuda_stream)
-            self._lib.check(self.lib.mwrt_push_async(C.c_void_p(self.dst[b][q]), C.c_void_p(src),
-                                                     self.rank_bytes, h), "push_async")
-            self._lib.check(self.lib.mwrt_push_async(C.c_void_p(self.dst_st[b][q]), C.c_void_p(src_st),
-                                                     self.st_bytes, h), "push_async")
+            st.wait_event(self.free[b])            # no rank still reads what buffer b held
+        self._push_slot(b, own.data_ptr(), self.status_g[b][self.rank].data_ptr())
+        for q, st in self.push.items():
             self.pushed[b][q].record(st)
         with torch.cuda.stream(self.comm):
             self.comm.wait_event(self.computed[b])
-            for q in self.peers:
+            for q in self.push:
                 self.comm.wait_event(self.pushed[b][q])
             self.hdl[b].barrier(channel=b)         # every rank's pushes of this step have landed everywhere
             self.landed[b].record(self.comm)
         self.step += 1
         return b
+
+    def wait(self, slot):
+        """Order the current stream after the arrival of every rank's results in `gathered[slot]`."""
+        torch.cuda.current_stream().wait_event(self.landed[slot])
 
     def finish(self):
         torch.cuda.current_stream().wait_stream(self.comm)
@@ -260,14 +323,19 @@ class CopyEngineGather:
         n = self.world * self.P_local
         if name in self.zero_fields:              # identically zero in clear sky; NaN where flagged
             out = torch.zeros((n, self.plan.Fo, self.plan.A), dtype=torch.float64, device=self.dev)
-            bad = (self.status_g[slot].reshape(n) & 11) != 0      # NAN_INPUT | NEG_ABS | RANGE
+            bad = (self.status(slot) & 11) != 0   # NAN_INPUT | NEG_ABS | RANGE
             out[bad] = float("nan")
             return out
         i = self.moved.index(name)
         return self.gathered[slot][:, i].reshape(n, self.plan.Fo, self.plan.A)
 
     def status(self, slot):
-        return self.status_g[slot].reshape(self.world * self.P_local)
+        return self.status_g[slot][:, :self.P_local].reshape(self.world * self.P_local)
+
+
+def CopyEngineGather(plan, P_local, fields, group=None):
+    """PushGather over the copy engines (one cudaMemcpyAsync per peer)."""
+    return PushGather(plan, P_local, fields, group=group, transport="ce")
 
 
 class FusedGatherForward:

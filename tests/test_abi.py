@@ -135,3 +135,16 @@ def test_hot_kernel_resource_budget(built_lib):
     assert k3["regs"] <= 170 and k3["spill_st"] == 0, k3
     k3bp = usage("_ZN4mwrt5k_rteILi10ELb1ELb1ELb0ELb0ELb1EEE")  # cloudy + fused band-pass: 384 threads/CTA
     assert k3bp["regs"] <= 170, k3bp
+
+
+def test_hostbind_never_raises_and_parses_cpulists():
+    """NUMA placement helper of the host entry point: pure host logic, must degrade to a no-op."""
+    from mwr_fast_forward_operators_and_lbls_b200 import hostbind
+    assert hostbind._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert hostbind._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    info = hostbind.bind_to_gpu_node(0)          # no GPU here: reports why, binds nothing
+    assert isinstance(info, dict) and "bound" in info
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)

@@ -57,6 +57,32 @@ def test_netcdf_contract_roundtrip(tmp_path):
     assert np.array_equal(np.asarray(back["Level_z"].values), lv["Level_z"])
 
 
+def test_driver_reads_level_variables_by_dimension_name():
+    """The reference indexes Level_* by name (`.isel(time=i).isel(Crop=j)`, PyRTlib_processing.py:109-114):
+    a dataset stored time-major must be unpacked exactly like one in contract order, and an unknown
+    dimension is an error instead of a silent level/profile swap."""
+    from mwr_fast_forward_operators_and_lbls_b200 import driver, io_formats as io
+    lv = _synth_level_dataset(T=3, C=2, L=24)
+    ds = io.SimpleDataset({k: (("N_Levels", "time", "Crop"), v) for k, v in lv.items()})
+    tm = io.SimpleDataset({k: (("time", "Crop", "N_Levels"), np.ascontiguousarray(v.transpose(1, 2, 0)))
+                           for k, v in lv.items()})
+    for k in lv:
+        assert np.array_equal(driver._level_values(ds, k), lv[k])
+        assert np.array_equal(driver._level_values(tm, k), lv[k])
+    bad = io.SimpleDataset({"Level_z": (("N_Levels", "time", "member"), lv["Level_z"])})
+    with pytest.raises(ValueError):
+        driver._level_values(bad, "Level_z")
+
+
+def test_builtin_model_tables_carry_their_provenance():
+    """The built-in line tables are not pinned to PyRTlib output: the package says so once per model
+    (warning) and the driver writes it into the output attributes."""
+    from mwr_fast_forward_operators_and_lbls_b200 import models
+    assert models.BUILTIN_TABLES_VERIFIED is False
+    note = models.provenance("R24")
+    assert "R24" in note and "NOT verified" in note
+
+
 def test_stats_oracle_matches_definition():
     rng = np.random.default_rng(2)
     v = rng.normal(150, 30, (40, 14))
@@ -86,6 +112,22 @@ def test_stats_gpu_vs_oracle(built_lib):
         assert np.allclose(sd.cpu().numpy()[:, k], o_sd, rtol=1e-12, atol=0)
         assert np.allclose(bias.cpu().numpy()[:, k], o_bias, rtol=1e-10, atol=1e-13)
         assert np.allclose(rmse.cpu().numpy()[:, k], o_rmse, rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
+def test_driver_output_attrs_carry_the_table_provenance(built_lib):
+    from mwr_fast_forward_operators_and_lbls_b200 import driver, io_formats as io
+    lv = _synth_level_dataset(T=2, C=2, L=24)
+    ds = io.SimpleDataset({k: (("time", "Crop", "N_Levels"), np.ascontiguousarray(v.transpose(1, 2, 0)))
+                           for k, v in lv.items()})               # time-major on purpose
+    ds["elevation"] = (("elevation",), np.array([90., 30.]))
+    ref = io.SimpleDataset({k: (("N_Levels", "time", "Crop"), v) for k, v in lv.items()})
+    ref["elevation"] = (("elevation",), np.array([90., 30.]))
+    ds, ref = driver.derive_TBs4PyRTlib(ds), driver.derive_TBs4PyRTlib(ref)
+    for model, var in io.OUTPUT_VARS:
+        assert "NOT verified" in ds[var].attrs["model_tables"] and ds[var].attrs["units"] == "K"
+        assert np.array_equal(ds[var].values, ref[var].values)
+        assert np.isfinite(ds[var].values).all()
 
 
 @pytest.mark.gpu
