@@ -615,3 +615,74 @@ def test_absorption_wide_frequency_blocks(pkg, ora, nf):
     awet, adry, _, _ = ora.pv.absorption("R22SD", d["p"], d["t"], e, frq)
     assert rel_err(cpu(g["awet"]), awet) < REL
     assert rel_err(cpu(g["adry"]), adry) < REL
+
+
+def test_no_out_of_bounds_writes_guard_bands(pkg):
+    """compute-sanitizer is closed on this GPU pool (profiles/r02_sanitizer_closed.log), so out-of-bounds
+    WRITES are hunted with guard bands instead: every output of every entry point is a window of a larger
+    buffer pre-filled with a sentinel bit pattern; after the kernels ran on awkward sizes (ragged tiles,
+    ragged warps, ragged channel groups) the bands before and after each window must be untouched and
+    the window itself fully overwritten."""
+    import torch
+    from mwr_fast_forward_operators_and_lbls_b200 import _lib
+    from mwr_fast_forward_operators_and_lbls_b200.forward import _ptr, _stream
+    lib = _lib.load()
+    SENT = -1.2345678912345e+200
+    G = 257                                                    # guard elements either side
+
+    def guarded(shape, dtype=torch.float64):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * G,), SENT if dtype == torch.float64 else -77, dtype=dtype, device="cuda")
+        return buf, buf[G:G + n].view(*shape)
+
+    def check(buf, n, name, must_fill=True):
+        sent = SENT if buf.dtype == torch.float64 else -77
+        assert bool((buf[:G] == sent).all()) and bool((buf[G + n:] == sent).all()), "guard band hit: " + name
+        if must_fill:
+            assert not bool((buf[G:G + n] == sent).any()), "window not fully written: " + name
+
+    P, L = 37, 33
+    d = pkg.synth_profiles(P, L, seed=5, clouds=True)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
+    cases = [("clear", dict(), pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, None),
+             ("cloudy+rt", dict(cloudy=True, ray_tracing=True), pkg.HATPRO_FRQ[:5], pkg.HATPRO_ELEV[:3], None),
+             ("bandpass 14x5", dict(cloudy=True), pkg.band_frequencies(5), pkg.HATPRO_ELEV, (14, 5, None)),
+             ("bandpass 3x7 ragged groups", dict(), pkg.band_frequencies(7, pkg.HATPRO_FRQ[:3], np.full(3, 0.2)),
+              pkg.HATPRO_ELEV[:7], (3, 7, None)),
+             ("tau_layers 130 freqs", dict(tau_layers=True), np.linspace(20, 60, 130), np.array([90.0, 30.0]), None),
+             ("fp32 line shape", dict(f32_lineshape=True), pkg.HATPRO_FRQ, pkg.HATPRO_ELEV[:4], None)]
+    for name, kw, frq, ang, bp in cases:
+        plan = pkg.Plan("R24", L, frq, ang, bandpass=bp, **kw)
+        bufs, out = {}, {}
+        for f in pkg.FIELDS:
+            bufs[f], out[f] = guarded((P, plan.Fo, plan.A))
+        bufs["status"], out["status"] = guarded((P,), torch.int32)
+        if kw.get("tau_layers"):
+            bufs["tau_layer"], out["tau_layer"] = guarded((P, plan.F, L))
+        plan.forward(dev["z"], dev["p"], dev["t"], dev["rh"], dev["denliq"] if plan.cloudy else None,
+                     dev["denice"] if plan.cloudy else None, out=out)
+        torch.cuda.synchronize()
+        for k, b in bufs.items():
+            check(b, out[k].numel(), "%s/%s" % (name, k))
+    # stage entry points
+    e, _ = pkg.vapor(dev["t"], dev["rh"])
+    frq = torch.from_numpy(np.ascontiguousarray(pkg.HATPRO_FRQ[:13])).cuda()
+    m = pkg.get_model("R22SD")
+    F = 13
+    b_w, awet = guarded((P, F, L))
+    b_d, adry = guarded((P, F, L))
+    b_l, aliq = guarded((P, F, L))
+    b_i, aice = guarded((P, F, L))
+    b_s, st = guarded((P,), torch.int32)
+    st.zero_()
+    _lib.check(lib.mwrt_absorption_f64(m.handle, P, L, F, _ptr(dev["p"]), _ptr(dev["t"]), _ptr(e), _ptr(dev["denliq"]),
+                                       _ptr(dev["denice"]), _ptr(frq), _ptr(awet), _ptr(adry), _ptr(aliq),
+                                       _ptr(aice), _ptr(st), _stream()), "absorption")
+    ang = torch.from_numpy(np.ascontiguousarray(pkg.HATPRO_ELEV[:7])).cuda()
+    b_ds, ds = guarded((P, 7, L))
+    _lib.check(lib.mwrt_slant_path_f64(P, L, 7, _ptr(dev["z"]), _ptr(dev["p"]), _ptr(dev["t"]), _ptr(e), _ptr(ang),
+                                       1, _ptr(ds), _ptr(st), _stream()), "slant_path")
+    torch.cuda.synchronize()
+    for b, n, nm in ((b_w, awet.numel(), "awet"), (b_d, adry.numel(), "adry"), (b_l, aliq.numel(), "aliq"),
+                     (b_i, aice.numel(), "aice"), (b_ds, ds.numel(), "ds"), (b_s, P, "status")):
+        check(b, n, "stage/" + nm)

@@ -1,5 +1,6 @@
 #!/bin/bash
 # compute-sanitizer on the smallest case that takes every kernel (tools/sanitize_target.py).
+# NOTE: on this GPU pool the tool answers "closed on this pool and stays closed" (profiles/r02_sanitizer_closed.log).
 # ONE tool per gpurun call (B200_PROFILING.md): tools/r02_call_sanitize.sh memcheck|racecheck|initcheck|synccheck
 T=${1:-memcheck}
 O=gpurun_out/r02s; mkdir -p $O
