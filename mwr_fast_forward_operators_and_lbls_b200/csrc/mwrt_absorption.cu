@@ -226,6 +226,9 @@ __host__ __device__ inline int abs_smem_doubles(int nh, int no, int FB) {
 #ifndef MWRT_ABS_MINB
 #define MWRT_ABS_MINB 4
 #endif
+#ifndef MWRT_ABS_O2_PIPELINE
+#define MWRT_ABS_O2_PIPELINE 1
+#endif
 #ifndef MWRT_ABS_WIDE_DEFAULT
 #define MWRT_ABS_WIDE_DEFAULT 1
 #endif
@@ -700,7 +703,79 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
 #pragma unroll
       for (int j = 0; j < FB; ++j) accf[j] = 0.0f;
     }
-    // The line strengths need one exp each.  They are evaluated G at a time, interleaved
+    // Narrow blocks (FB <= 16): SOFTWARE PIPELINE over the line pairs -- the hoisted parameters of pair
+    // k+1 (two strength exps and ~45 dependent FP64 operations: a latency-bound chain) are computed in
+    // the same basic block as the frequency loop of pair k (FB independent chains: throughput-bound), so
+    // the scheduler fills the chain's stalls with the loop's work; only the 8-10 doubles of the next
+    // pair are carried, the rare correction path recomputes its line state.  Measured on B200
+    // (profiles/r02j_variants.txt): 0.804 -> 0.776 ms for config 2, bit-identical; with 28/32-wide blocks
+    // the loop already hides what there is to hide and the extra live registers cost 5-6 %, and the same
+    // pipeline over the H2O pairs (six exps and two line states in flight) is slower everywhere (0.87 ms)
+    // -- both keep the plain form.  The two forms are kept as two verbatim code paths (no shared
+    // helpers): sharing them through lambdas changed the register allocation of BOTH and lost the gain.
+    constexpr bool kO2Pipe = (FB <= 16) && (MWRT_ABS_O2_PIPELINE != 0);
+    if constexpr (kO2Pipe) {
+      struct O2Pair { double c3a, c4a, n1a, n0a, ba, c3b, c4b, n1b, n0b, bb; };
+      auto pair_hot = [&](int k) {
+        double ea[2], ev[2];
+        ea[0] = -orow[k * kOS + MWRT_O2_BE] * th1;
+        ea[1] = -orow[(k + 1) * kOS + MWRT_O2_BE] * th1;
+        exp_tb_vec<2>(ea, ev, etab);
+        const O2Line a = hoist(k, ev[0]), c = hoist(k + 1, ev[1]);
+        return O2Pair{a.c3, a.c4, a.n1, a.n0, a.b32, c.c3, c.c4, c.n1, c.n0, c.b32};
+      };
+      O2Pair cur = pair_hot(0);
+#pragma unroll 1
+      for (int k = 0; k < nop; k += 2) {
+        const O2Pair nxt = pair_hot(k + 2 < nop ? k + 2 : k);   // (last pass: recomputed and dropped)
+        if constexpr (F32) {
+          const PairHotF h{(float)cur.ba, (float)cur.c4a, (float)(cur.n1a * kF32Scale), (float)(cur.n0a * kF32Scale),
+                           (float)cur.bb, (float)cur.c4b, (float)(cur.n1b * kF32Scale), (float)(cur.n0b * kF32Scale)};
+          pair_accumulate_f32<FB>(accf, a32o + k * FBP, a32o + (k + 1) * FBP, h);
+        } else {
+          const PairHot h{cur.c3a, cur.c4a, cur.n1a, cur.n0a, cur.c3b, cur.c4b, cur.n1b, cur.n0b};
+          pair_accumulate<FB>(acc, fsq2, h);
+        }
+        cur = nxt;
+        // rare: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency
+        if (!(ochk[k] | ochk[k + 1])) continue;   // uniform, decided per CTA
+        const double expa = exp_tb_(-orow[k * kOS + MWRT_O2_BE] * th1);
+        const double expb = exp_tb_(-orow[(k + 1) * kOS + MWRT_O2_BE] * th1);
+        const O2Line oa = hoist(k, expa);
+        const O2Line ob = hoist(k + 1, expb);
+        const double fka = orow[k * kOS + MWRT_O2_F], fkb = orow[(k + 1) * kOS + MWRT_O2_F];
+        const bool sda = m.o2_sd118 && k == 0 && (f_lo - oa.fcen < 10.0 * oa.df) &&
+                         (oa.fcen - f_hi < 10.0 * oa.df);
+        const bool nwa = (oa.df < 1e-3 * fka) && (dmino[k] - fabs(oa.fcen - fka) < 1e-3 * fka);
+        const bool nwb = (ob.df < 1e-3 * fkb) && (dmino[k + 1] - fabs(ob.fcen - fkb) < 1e-3 * fkb);
+        const int ca = (sda || nwa) ? 1 : 0, cb = nwb ? 1 : 0;
+        if (!(ca | cb)) continue;
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s) {
+          if (!(s ? cb : ca)) continue;
+          const int kk = k + s;
+          const bool sd = sda && s == 0;
+          const O2Line g = hoist(kk, s ? expb : expa);   // full line state, recomputed
+#pragma unroll 1
+          for (int j = 0; j < FB; ++j) {
+            const double d1 = fblk[j] - g.fcen;
+            const double d2 = fblk[j] + g.fcen;
+            double sf1;
+            if (sd && fabs(d1) < 10.0 * g.df)
+              sf1 = o2_sd118_sf1(g.df, d1, g.y);
+            else
+              sf1 = div_fast(g.df * g.gfac + d1 * g.y, fma(d1, d1, g.df2));
+            const double sf2 = div_fast(g.df * g.gfac - d2 * g.y, fma(d2, d2, g.df2));
+            const double vv = fsq[j] - g.c3;
+            const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
+            tmp[j] = fma(g.sp, sf1 + sf2, -fast);
+          }
+#pragma unroll
+          for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
+        }
+      }   // pairs
+    } else {
+    // Wide blocks: the line strengths need one exp each.  They are evaluated G at a time, interleaved
     // (exp_tb_vec), so the FP64 pipe sees G independent chains; the values are handed to the pair
     // loop by rotating a small register array (no dynamic indexing).
     constexpr int G = 6;
@@ -762,6 +837,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
         }
       }   // pairs of the group
     }     // groups
+    }
     const double scale = m.o2_abs_const * presda * (th * th * th);
     const double pdry_mb = pdrykpa * 10.0;
     const double n2base = m.n2_n * (m.n2_l * pdry_mb * pdry_mb * exp_tb_(m.n2_m * thln));

@@ -9,7 +9,7 @@ mkdir -p $V
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xptxas -v --fmad=true "$@" \
   -c $C/mwrt_$tu.cu -o $V/${tu}_$name.o > $V/${tu}_$name.log 2>&1
 objs=""
-for t in api absorption rte rte_fanout post peak; do
+for t in api absorption rte rte_fanout post peak push; do
   if [ "$t" == "$tu" ]; then objs="$objs $V/${tu}_$name.o"; else objs="$objs $C/mwrt_$t.o"; fi
 done
 nvcc -shared -o $V/libmwrt_$name.so $objs -gencode arch=compute_100a,code=sm_100a -cudart static
