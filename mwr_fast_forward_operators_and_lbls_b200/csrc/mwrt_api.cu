@@ -502,6 +502,10 @@ int mwrt_plan_set_bandpass(mwrt_plan* pl, int C, int S, const double* weights) {
   }
   pl->C = C; pl->S = S;
   pl->bp_cpb = rte_bp_channels_per_cta(C, S);   // 0: a sub-band does not fit one CTA -> unfused fallback
+  if (const char* e = getenv("MWRT_BP_CPB")) {   // tuning knob: fewer channels per CTA (more, smaller CTAs per SM)
+    const int want = atoi(e);
+    if (want >= 1 && want < pl->bp_cpb) pl->bp_cpb = want;
+  }
   return 0;
 }
 
