@@ -723,6 +723,10 @@ int mwrt_plan_forward_host(mwrt_plan* pl, int P, const mwrt_profiles* in, const 
   static const int env_pieces = [] { const char* e = getenv("MWRT_HOST_PIECES"); return e ? atoi(e) : 0; }();
   const int pieces = env_pieces > 0 ? env_pieces : (pl->split > 1 ? 2 * pl->split : 12);
   int chunk = std::min(pl->chunk, std::max((P + pieces - 1) / pieces, env_pieces > 0 ? 256 : 1024));
+  if (const char* ce = getenv("MWRT_HOST_CHUNK")) {   // tuning knob: explicit chunk size in profiles
+    const int want = atoi(ce);
+    if (want >= 64) chunk = std::min(pl->chunk, want);
+  }
   chunk = std::min(chunk, P);
   std::vector<int> sizes;
   for (int left = P; left > 0; left -= sizes.back()) sizes.push_back(std::min(chunk, left));
