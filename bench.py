@@ -185,28 +185,54 @@ def build_config(pkg, cfg, rank, world, scale=1.0):
     return dict(plan=plan, d=d, Ptot=Ptot, P=b - a, L=L, F=len(frq), A=len(ang), fields=fields, kw=kw)
 
 
-def run_config(pkg, cfg, rank, world, reps=3, scale=1.0):
-    """One BASELINE configuration at full size over `world` ranks: every rank computes its shard, the
-    (P,Fo,A) results are all-gathered (one NCCL collective of the stacked fields per pass, inside the
-    timing); config 4's 48 GB per-layer optical depth stays sharded (each rank keeps its block).
+def run_config(pkg, cfg, rank, world, reps=3, scale=1.0, gather="push", pieces=4):
+    """One BASELINE configuration at full size over `world` ranks: every rank computes its shard and the
+    (P,Fo,A) results end up on EVERY rank, inside the timing -- by default pushed piece by piece while
+    the next piece computes (distributed.PushGatherPass; checked once against an NCCL all-gather of the
+    same fields), with gather="nccl" by one all_gather_into_tensor after the kernels.  Config 4's 48 GB
+    per-layer optical depth stays sharded (each rank keeps its block).
     Time = CUDA events around a pass, median of `reps`, max over ranks."""
     import numpy as np
     import torch
     import torch.distributed as dist
     from mwr_fast_forward_operators_and_lbls_b200 import roofline
+    from mwr_fast_forward_operators_and_lbls_b200.distributed import PushGatherPass
     c = build_config(pkg, cfg, rank, world, scale)
     plan, d, fields = c["plan"], c["d"], c["fields"]
     P, Ptot, L, F, A = c["P"], c["Ptot"], c["L"], c["F"], c["A"]
     dev = {k: torch.from_numpy(v).cuda() for k, v in d.items()}
     nf, Fo = len(fields), plan.Fo
     pmax = -(-Ptot // world)
-    stacked = torch.zeros((pmax, nf, Fo, A), dtype=torch.float64, device="cuda")   # padded to the largest shard
+    local_out = {}
+    if c["kw"].get("tau_layers"):
+        local_out["tau_layer"] = torch.empty((P, F, L), dtype=torch.float64, device="cuda")
+    pg, how = None, "single GPU"
+    if world > 1 and gather == "push" and Ptot % world == 0:
+        try:
+            pg = PushGatherPass(plan, P, fields, pieces=pieces)
+            how = ("push gather in %d pieces (%s), overlapped with the kernels of the next piece; all ranks hold "
+                   "the (P,Fo,A) fields" % (pg.pieces, pg.transport))
+        except Exception as exc:      # no symmetric memory: plain NCCL
+            if rank == 0:
+                print("push gather unavailable for config %d (%r); using NCCL" % (cfg, exc), file=sys.stderr)
+            pg = None
     out = {k: torch.empty((P, Fo, A), dtype=torch.float64, device="cuda") for k in fields}
     out["status"] = torch.empty((P,), dtype=torch.int32, device="cuda")
-    if c["kw"].get("tau_layers"):
-        out["tau_layer"] = torch.empty((P, F, L), dtype=torch.float64, device="cuda")
-    full = torch.empty((world * pmax, nf, Fo, A), dtype=torch.float64, device="cuda") if world > 1 else None
+    out.update(local_out)
+    stacked = full = None
+    if world > 1:
+        stacked = torch.zeros((pmax, nf, Fo, A), dtype=torch.float64, device="cuda")   # padded to the largest shard
+        full = torch.empty((world * pmax, nf, Fo, A), dtype=torch.float64, device="cuda")
+        if pg is None:
+            how = "one all_gather_into_tensor of the stacked fields after the kernels; all ranks hold the (P,Fo,A) fields"
 
+    def nccl_pass():
+        plan.forward(dev["z"], dev["p"], dev["t"], dev["rh"], dev.get("denliq"), dev.get("denice"),
+                     fields=fields, out=out)
+        if world > 1:
+            for i, k in enumerate(fields):
+                stacked[:P, i].copy_(out[k])
+            dist.all_gather_into_tensor(full, stacked)
     ts, tc = [], []
     for it in range(1 + reps):
         if world > 1:
@@ -214,13 +240,18 @@ def run_config(pkg, cfg, rank, world, reps=3, scale=1.0):
         torch.cuda.synchronize()
         e0, em, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         e0.record()
-        plan.forward(dev["z"], dev["p"], dev["t"], dev["rh"], dev.get("denliq"), dev.get("denice"),
-                     fields=fields, out=out)
-        em.record()
-        if world > 1:
-            for i, k in enumerate(fields):
-                stacked[:P, i].copy_(out[k])
-            dist.all_gather_into_tensor(full, stacked)
+        if pg is not None:
+            pg.run(dev["z"], dev["p"], dev["t"], dev["rh"], dev.get("denliq"), dev.get("denice"), local_out=local_out)
+            em.record()
+            pg.finish()
+        else:
+            plan.forward(dev["z"], dev["p"], dev["t"], dev["rh"], dev.get("denliq"), dev.get("denice"),
+                         fields=fields, out=out)
+            em.record()
+            if world > 1:
+                for i, k in enumerate(fields):
+                    stacked[:P, i].copy_(out[k])
+                dist.all_gather_into_tensor(full, stacked)
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1), e0.elapsed_time(em)], dtype=torch.float64, device="cuda")
@@ -230,7 +261,23 @@ def run_config(pkg, cfg, rank, world, reps=3, scale=1.0):
             ts.append(float(t[0].item()))
             tc.append(float(t[1].item()))
     ms = float(np.median(ts))
-    finite = bool(torch.isfinite(out["tbtotal"]).all().item())
+    identical = None
+    if pg is not None:      # the pushed result against NCCL's, once, outside the timing
+        nccl_pass()
+        torch.cuda.synchronize()
+        same = True
+        for i, k in enumerate(fields):
+            ref = full[:, i].reshape(world, P, Fo, A)
+            got = pg.field(k)                                  # (world, pieces, Pp, Fo, A)
+            got = got.reshape(world, pg.pieces * pg.Pp, Fo, A)[:, :P]
+            same = same and bool(torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref, nan=-7.0)))
+        flag = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        identical = bool(flag.item())
+        tb_ref = pg.field("tbtotal")
+        finite = bool(torch.isfinite(tb_ref.reshape(world, -1, Fo, A)[:, :P]).all().item())
+    else:
+        finite = bool(torch.isfinite(out["tbtotal"]).all().item())
     w = roofline.work(Ptot, L, F, A, cloudy=c["kw"].get("cloudy", False), tau_layers=c["kw"].get("tau_layers", False))
     res = {"config": CONFIG_NAMES[cfg], "profiles_total": Ptot, "profiles_per_rank": P, "levels": L,
            "frequencies": F, "channels_out": Fo, "elevations": A, "n_gpus": world, "ms_per_pass": ms,
@@ -238,13 +285,13 @@ def run_config(pkg, cfg, rank, world, reps=3, scale=1.0):
            "all_ms": ts, "tb_per_s": Ptot * Fo * A / ms * 1e3, "mono_tb_per_s": Ptot * F * A / ms * 1e3,
            "algorithmic_tflops": w["flops_total"] / ms / 1e9,
            "algorithmic_tflops_per_gpu": w["flops_total"] / ms / 1e9 / world,
-           "gathered": "all ranks hold the (P,Fo,A) fields" + ("; tau_layer stays sharded" if cfg == 4 else "")
-                       if world > 1 else "single GPU",
+           "gathered": how + ("; tau_layer stays sharded" if cfg == 4 and world > 1 else ""),
+           "gather_identical_to_nccl": identical,
            "launches_per_pass_per_rank": plan.launch_count(P), "finite": finite}
     if cfg == 4:
         res["tau_layer_gbytes"] = 8.0 * Ptot * F * L / 1e9
         res["tau_layer_gbs"] = 8.0 * Ptot * F * L / ms / 1e6
-    del plan, dev, out, stacked, full
+    del plan, dev, out, stacked, full, pg
     torch.cuda.empty_cache()
     return res
 
@@ -304,7 +351,8 @@ def main():
     N = world
 
     if args.config != 2:       # another configuration as the line (builder runs; the driver uses the default)
-        r = run_config(pkg, args.config, rank, world, reps=max(3, min(args.steps, 10)), scale=args.scale)
+        r = run_config(pkg, args.config, rank, world, reps=max(3, min(args.steps, 10)), scale=args.scale,
+                       gather="nccl" if args.gather == "nccl" else "push")
         if rank == 0:
             _emit({"metric": METRIC, "value": r["tb_per_s"], "unit": UNIT, "n_gpus": N, "steps": len(r["all_ms"]),
                    "warmup": 1, "ms_per_step": r["ms_per_pass"], "higher_is_better": True, "scaling": "strong",
@@ -569,7 +617,8 @@ def main():
         cfgs = []
         for cfg in (3, 5, 4):
             try:
-                cfgs.append(run_config(pkg, cfg, rank, world, reps=3, scale=args.scale))
+                cfgs.append(run_config(pkg, cfg, rank, world, reps=3, scale=args.scale,
+                                       gather="nccl" if args.gather == "nccl" else "push"))
             except Exception as exc:      # e.g. out of memory on a smaller part: say so, keep the line
                 cfgs.append({"config": CONFIG_NAMES[cfg], "error": repr(exc)})
                 torch.cuda.empty_cache()

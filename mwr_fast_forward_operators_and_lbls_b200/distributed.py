@@ -338,6 +338,147 @@ def CopyEngineGather(plan, P_local, fields, group=None):
     return PushGather(plan, P_local, fields, group=group, transport="ce")
 
 
+class PushGatherPass:
+    """ONE pass over a rank's shard, cut into `pieces`: piece c is pushed into every peer's gathered
+    buffer (same transports as `PushGather`) while piece c+1 is being computed, so that a pass costs
+    max(kernels, gather) + one piece instead of kernels + gather.  For the strong-scaling
+    configurations (BASELINE.json configs 3-5 split over the ranks), where a single all-gather at the
+    end of the pass is fully exposed: config 5 on 8 GPUs gathers 3.4 GB of results to every rank, as
+    long as its kernels take.
+
+    Layout: `gathered` is (world, pieces, nfield, Pp, F, A) with Pp = ceil(P_local / pieces) -- one
+    contiguous block per (rank, piece), written in place by kernel 3.  A ragged last piece leaves its
+    unused rows unspecified.  `field(name)` is the (world, pieces, Pp, F, A) view; `valid_rows(c)` the
+    number of profiles of piece c.  Every rank must pass the same P_local.  As in `PushGather`, `run()`
+    starts with an entry barrier: consume a pass's results before calling `run()` again.
+    """
+
+    def __init__(self, plan, P_local, fields, pieces=4, group=None, transport="auto", nblocks=0):
+        import os
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib, self.lib = _lib, _lib.load()
+        self.plan, self.fields = plan, tuple(fields)
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.P_local = int(P_local)
+        pieces = max(1, min(int(pieces), self.P_local))
+        self.Pp = -(-self.P_local // pieces)
+        self.pieces = -(-self.P_local // self.Pp)
+        F, A = plan.Fo, plan.A
+        zero = () if plan.cloudy else ("tauliq", "tauice")
+        self.moved = tuple(f for f in self.fields if f not in zero)
+        self.zero_fields = tuple(f for f in self.fields if f in zero)
+        nf = len(self.moved)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        self.Pp_pad = (self.Pp + 3) & ~3
+        self.gathered = symm_mem.empty((self.world, self.pieces, nf, self.Pp, F, A), dtype=torch.float64, device=dev)
+        self.hdl = symm_mem.rendezvous(self.gathered, self.group)
+        self.status_g = symm_mem.empty((self.world, self.pieces, self.Pp_pad), dtype=torch.int32, device=dev)
+        self.hdl_st = symm_mem.rendezvous(self.status_g, self.group)
+        self.status_g.zero_()
+        self.piece_bytes = nf * self.Pp * F * A * 8
+        self.st_bytes = self.Pp_pad * 4
+        mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in (self.hdl, self.hdl_st)]
+        if transport == "auto":
+            transport = "multicast" if (self.world > 4 and all(mc) and self.piece_bytes % 16 == 0) else "ce"
+        if transport == "multicast" and not all(mc):
+            raise RuntimeError("NVLink multicast is not available for this group")
+        if transport in ("multicast", "peers") and self.piece_bytes % 16:
+            raise RuntimeError("the push kernel moves 16-byte words; a piece has %d bytes" % self.piece_bytes)
+        self.transport = transport
+        self.nblocks = int(nblocks or os.environ.get("MWRT_PUSH_BLOCKS", 0) or 8)
+        self.peers = [q for q in range(self.world) if q != self.rank]
+        self.base = {q: int(self.hdl.buffer_ptrs[q]) for q in self.peers}
+        self.base_st = {q: int(self.hdl_st.buffer_ptrs[q]) for q in self.peers}
+        self.mc, self.mc_st = mc
+        if transport == "ce":
+            self.push = {q: torch.cuda.Stream() for q in self.peers}
+        else:
+            self.push = {None: torch.cuda.Stream(priority=-1)}
+        self.comm = torch.cuda.Stream(priority=-1)
+        self.computed = [torch.cuda.Event() for _ in range(self.pieces)]
+        self.entered, self.free, self.landed = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.passes = 0
+
+    def valid_rows(self, c):
+        return min(self.P_local, (c + 1) * self.Pp) - c * self.Pp
+
+    def _push(self, c):
+        chk, lib = self._lib.check, self.lib
+        off = (self.rank * self.pieces + c) * self.piece_bytes
+        off_st = (self.rank * self.pieces + c) * self.st_bytes
+        src = self.gathered[self.rank, c].data_ptr()
+        src_st = self.status_g[self.rank, c].data_ptr()
+        if self.transport == "ce":
+            for q in self.peers:
+                h = C.c_void_p(self.push[q].cuda_stream)
+                chk(lib.mwrt_push_async(C.c_void_p(self.base[q] + off), C.c_void_p(src), self.piece_bytes, h), "push_async")
+                chk(lib.mwrt_push_async(C.c_void_p(self.base_st[q] + off_st), C.c_void_p(src_st), self.st_bytes, h),
+                    "push_async")
+            return
+        h = C.c_void_p(self.push[None].cuda_stream)
+        if self.transport == "multicast":
+            chk(lib.mwrt_push_kernel(C.c_void_p(src), self.piece_bytes, C.c_void_p(self.mc + off), None, 0,
+                                     self.nblocks, h), "push_kernel")
+            chk(lib.mwrt_push_kernel(C.c_void_p(src_st), self.st_bytes, C.c_void_p(self.mc_st + off_st), None, 0, 1, h),
+                "push_kernel")
+        else:
+            n = len(self.peers)
+            arr = (C.c_int64 * n)(*[self.base[q] + off for q in self.peers])
+            chk(lib.mwrt_push_kernel(C.c_void_p(src), self.piece_bytes, None, arr, n, self.nblocks, h), "push_kernel")
+            arr = (C.c_int64 * n)(*[self.base_st[q] + off_st for q in self.peers])
+            chk(lib.mwrt_push_kernel(C.c_void_p(src_st), self.st_bytes, None, arr, n, 1, h), "push_kernel")
+
+    def run(self, z, p, t, rh, denliq=None, denice=None, local_out=None):
+        """`local_out`: dict of full-size (P_local, ...) tensors that stay on this rank (e.g. 'tau_layer'),
+        sliced per piece."""
+        main = torch.cuda.current_stream()
+        self.entered.record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.entered)
+            self.hdl_st.barrier(channel=0)          # every rank is past the consumers of the previous pass
+            self.free.record(self.comm)
+        if self.passes > 0:
+            main.wait_event(self.landed)            # my pushes of the previous pass have left my slots
+        for c in range(self.pieces):
+            a = c * self.Pp
+            n = self.valid_rows(c)
+            own = self.gathered[self.rank, c]       # (nf, Pp, F, A)
+            out = {k: own[i, :n] for i, k in enumerate(self.moved)}
+            out["status"] = self.status_g[self.rank, c, :n]
+            for k, v in (local_out or {}).items():
+                out[k] = v[a:a + n]
+            self.plan.forward(z[a:a + n], p[a:a + n], t[a:a + n], rh[a:a + n],
+                              None if denliq is None else denliq[a:a + n],
+                              None if denice is None else denice[a:a + n], fields=self.moved, out=out)
+            self.computed[c].record(main)
+            for st in self.push.values():
+                st.wait_event(self.computed[c])
+                if c == 0:
+                    st.wait_event(self.free)
+            self._push(c)
+        with torch.cuda.stream(self.comm):
+            for st in self.push.values():
+                self.comm.wait_stream(st)
+            self.hdl.barrier(channel=0)             # every rank's pieces have landed everywhere
+            self.landed.record(self.comm)
+        self.passes += 1
+
+    def finish(self):
+        torch.cuda.current_stream().wait_event(self.landed)
+
+    def field(self, name):
+        """(world, pieces, Pp, F, A) view of one gathered field (rank-major, then piece, then local index)."""
+        if name in self.zero_fields:
+            out = torch.zeros((self.world, self.pieces, self.Pp, self.plan.Fo, self.plan.A), dtype=torch.float64,
+                              device=self.dev)
+            out[(self.status_g[:, :, :self.Pp] & 11) != 0] = float("nan")
+            return out
+        return self.gathered[:, :, self.moved.index(name)]
+
+
 class FusedGatherForward:
     """The gather fused into kernel 3: every rank's RTE kernel stores its results straight into the
     gathered buffer of ALL ranks -- with NVLink multicast stores (`multimem.st`: one store, NVSwitch
