@@ -686,3 +686,55 @@ def test_no_out_of_bounds_writes_guard_bands(pkg):
     for b, n, nm in ((b_w, awet.numel(), "awet"), (b_d, adry.numel(), "adry"), (b_l, aliq.numel(), "aliq"),
                      (b_i, aice.numel(), "aice"), (b_ds, ds.numel(), "ds"), (b_s, P, "status")):
         check(b, n, "stage/" + nm)
+
+
+@pytest.mark.parametrize("P,L,F,A", [(1, 2, 1, 1), (3, 5, 2, 3), (2, 300, 3, 11), (1, 50, 17, 20),
+                                     (129, 33, 15, 7), (5, 100, 29, 2)])
+@pytest.mark.parametrize("mode", ["plane", "raytraced", "cloudy", "upwelling"])
+def test_edge_shapes_against_oracle(pkg, ora, P, L, F, A, mode):
+    """Smallest and most awkward shapes of every variant: 2 levels (one layer), one frequency / angle,
+    more angles than a register tile holds (11, 20 -> two angle groups), frequency counts that are no
+    multiple of any block width, level counts beyond a warp round of the slant path (300), tile- and
+    warp-ragged batches (129 x 33)."""
+    Lg = max(L, 5)                                         # (the generator needs a few levels to smooth over)
+    d = pkg.synth_profiles(P, Lg, seed=100 + P + L, clouds=(mode == "cloudy"))
+    pick = np.unique(np.linspace(0, Lg - 1, L).round().astype(int))
+    d = {k: np.ascontiguousarray(v[:, pick]) for k, v in d.items()}
+    frq = np.linspace(20.0, 61.0, F) if F > 1 else np.array([31.4])
+    ang = np.linspace(90.0, 4.2, A) if A > 1 else np.array([19.2])
+    if mode == "raytraced":
+        ang = np.clip(ang, 4.2, 88.5)                      # (upstream takes 89-91 deg as the vertical)
+    kw = dict(ray_tracing=(mode == "raytraced"), from_sat=(mode == "upwelling"))
+    if mode == "cloudy":
+        kw.update(denliq=d["denliq"], denice=np.where(d["t"] < 250.0, 0.01, 0.0))
+    out = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], frq, ang, "R24", **kw)
+    ref = ora.pv.simulate(d["z"], d["p"], d["t"], d["rh"], frq, ang, "R24", **kw)
+    for k in ("tbtotal", "tbatm", "tmr"):
+        assert np.max(np.abs(cpu(out[k]) - ref[k])) < TB_ABS, k
+    for k in ("tauwet", "taudry", "tauliq", "tauice"):
+        assert rel_err(cpu(out[k]), ref[k], floor=1e-30) < REL, k
+    assert (cpu(out["status"]) == 0).all()
+
+
+def test_physics_invariants_on_the_gpu(pkg):
+    """SURVEY.md Appendix D on the CUDA path itself: dry air -> tau_wet = 0 exactly; no cloud water ->
+    tau_liq = tau_ice = 0 exactly on a cloudy plan; an almost empty atmosphere -> TB -> the cosmic
+    background (Planck-consistent, 2.736 K); results do not depend (beyond rounding) on the other angles
+    or frequencies a profile is evaluated with."""
+    import torch
+    d = pkg.synth_profiles(6, 60, seed=9)
+    zero = np.zeros_like(d["rh"])
+    out = pkg.simulate(d["z"], d["p"], d["t"], zero, pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, "R24")
+    assert (cpu(out["tauwet"]) == 0.0).all() and np.isfinite(cpu(out["tbtotal"])).all()
+    out = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, "R24",
+                       denliq=zero, denice=zero)
+    clr = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ, pkg.HATPRO_ELEV, "R24")
+    assert (cpu(out["tauliq"]) == 0.0).all() and (cpu(out["tauice"]) == 0.0).all()
+    assert np.array_equal(cpu(out["tbtotal"]), cpu(clr["tbtotal"]))
+    thin = pkg.simulate(d["z"], d["p"] * 1e-7, d["t"], zero, [31.4], [90.0], "R24")
+    assert np.max(np.abs(cpu(thin["tbtotal"]) - 2.736)) < 1e-6
+    one = pkg.simulate(d["z"], d["p"], d["t"], d["rh"], pkg.HATPRO_FRQ[3:4], pkg.HATPRO_ELEV[5:6], "R24")
+    # (a different frequency-block width and angle tile compile to different instruction orders:
+    # agreement to rounding, not bit for bit)
+    assert np.max(np.abs(cpu(one["tbtotal"])[:, 0, 0] - cpu(clr["tbtotal"])[:, 3, 5])) < 1e-9
+    del torch
