@@ -28,7 +28,10 @@ namespace mwrt {
 
 #define exp_tb_(x) exp_tb((x), etab)   // etab: the kernel's shared-memory exp table
 
-constexpr int kAbsThreads = 128;
+#ifndef MWRT_ABS_THREADS
+#define MWRT_ABS_THREADS 128   // measured: 64 and 256 threads per CTA (same warps per SM) are not faster
+#endif
+constexpr int kAbsThreads = MWRT_ABS_THREADS;
 constexpr int kAllIn = 0, kAllOut = 1, kWing1Out = 2, kMixed = 3;
 
 // rare-path helpers are kept out of line: the hot loops must stay small enough for the

@@ -4,7 +4,10 @@
 
 namespace mwrt {
 
-constexpr int kRteThreads = 128;
+#ifndef MWRT_RTE_THREADS
+#define MWRT_RTE_THREADS 128
+#endif
+constexpr int kRteThreads = MWRT_RTE_THREADS;
 constexpr int kRteBpMaxThreads = 384;   // fused band-pass: one CTA = whole channels, <= this many sub-frequencies
 
 // Everything kernel 3 is given, as one by-value argument (the launcher family passes it through).
