@@ -164,6 +164,14 @@ int mwrt_plan_set_emissivity(mwrt_plan* plan, double es);
 #define MWRT_PREC_F64 0
 #define MWRT_PREC_F32_LINESHAPE 1
 int mwrt_plan_set_precision(mwrt_plan* plan, int precision);
+/* Kernel 1 alone on a plan's frequency list, model and precision: awet, adry (P,F,L) from p, tk, e (P,L),
+ * all DEVICE memory, status (P,) OR-ed or NULL.  Same results as mwrt_absorption_f64 / _f32ls, but the
+ * per-frequency-block tables kernel 1 reads are the plan's cached ones instead of being rebuilt per call
+ * (the stage of TbCloudRTE.execute() that PyRTlib runs as RTEquation.clearsky_absorption per angle and
+ * frequency; reached by the reference at python_src/proc/PyRTlib_processing.py:126).  This is the call
+ * bench.py times for the roofline figure. */
+int mwrt_plan_absorption(mwrt_plan* plan, int P, const double* p, const double* tk, const double* e,
+                         double* awet, double* adry, int32_t* status, void* stream);
 /* pieces > 1: mwrt_plan_forward_device cuts the batch into `pieces` parts and overlaps kernel 3 of
  * part c (on a stream owned by the plan) with kernel 1 of part c+1 (on the caller's stream); the
  * caller's stream still completes after everything.  The host entry point runs equal chunks of ~1000

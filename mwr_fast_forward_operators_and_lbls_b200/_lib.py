@@ -65,6 +65,7 @@ SYMBOLS = {
     "mwrt_plan_destroy": (C.c_int, [C.c_void_p]),
     "mwrt_plan_set_emissivity": (C.c_int, [C.c_void_p, C.c_double]),
     "mwrt_plan_set_precision": (C.c_int, [C.c_void_p, C.c_int]),
+    "mwrt_plan_absorption": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 7),
     "mwrt_plan_set_split": (C.c_int, [C.c_void_p, C.c_int]),
     "mwrt_plan_set_bandpass": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_dp]),
     "mwrt_plan_launch_count": (C.c_int, [C.c_void_p, C.c_int]),

@@ -23,6 +23,7 @@
 #include "mwrt_common.cuh"
 #include "mwrt_cloud.cuh"
 #include <stdlib.h>
+#include <mutex>
 
 namespace mwrt {
 
@@ -32,7 +33,7 @@ namespace mwrt {
 #define MWRT_ABS_THREADS 128   // measured: 64 and 256 threads per CTA (same warps per SM) are not faster
 #endif
 constexpr int kAbsThreads = MWRT_ABS_THREADS;
-constexpr int kAllIn = 0, kAllOut = 1, kWing1Out = 2, kMixed = 3;
+constexpr int kAllIn = 0, kAllOut = 1, kWing1Out = 2, kMixed = 3, kFarIn = 4;
 
 // rare-path helpers are kept out of line: the hot loops must stay small enough for the
 // instruction caches (the first version inlined them 14x and stalled on instruction fetch)
@@ -219,10 +220,64 @@ __device__ __forceinline__ void pair_accumulate(double (&acc)[FB], const double2
 static_assert(kHS % 2 == 0 && kOS % 2 == 0, "row strides must keep 16-byte alignment");
 constexpr int kSlowNone = 0, kSlowCorr = 1, kSlowExact = 2;
 
+// ---- far lines on a coarse grid ------------------------------------------------------------------
+// A line whose centre is far from the block's frequencies (in units of the block's own width) is a very
+// smooth function of u = f^2 across the block: its poles sit at u = c3 +/- i sqrt(c4), a distance
+// |c3 - u0| >= rho * h away from the block [u0 - h, u0 + h].  The SUM of all such lines is evaluated
+// with the same pair loop at kNQ Chebyshev nodes of the block instead of at its FB frequencies and
+// interpolated once per level-point (Lagrange weights, tabulated per CTA): kNQ instead of FB
+// evaluations per far line.  Interpolation error <= ~2 (rho + sqrt(rho^2-1))^-kNQ of the far lines'
+// own contribution; kFarRho is chosen so that this is 1e-11 (two orders inside the 1e-9 parity gate;
+// measured against the oracle: <= 8e-12 of the line sum, tests/test_kernel_algebra.py).  The decision is
+// per CTA from the table centres with margins for the pressure shift (the 1 GHz the fast form allows)
+// and the width (w^2 <= 37 GHz^2).  HATPRO (14 channels, one block): 12 of 14 H2O and 11 of 49 O2 lines
+// are far; a 28- or 32-wide block of a dense spectrum sees nearly every line as far.
+#ifndef MWRT_ABS_NQ
+#define MWRT_ABS_NQ 6
+#endif
+constexpr int kNQ = MWRT_ABS_NQ;
+static_assert(kNQ == 4 || kNQ == 6 || kNQ == 8, "node count: even (rows are read with LDS.128)");
+constexpr double kFarRho = kNQ == 4 ? 282.0 : (kNQ == 6 ? 34.1 : 11.9);   // 10^(11/kNQ) = rho + sqrt(rho^2 - 1)
+#ifndef MWRT_ABS_FAR_BUILD
+#define MWRT_ABS_FAR_BUILD 1   // 0 compiles the far-line code out (tuning experiments)
+#endif
+#ifndef MWRT_ABS_FAR_MINFB
+#define MWRT_ABS_FAR_MINFB 17  // narrowest block that carries the far-line code
+#endif
+// The far-line code is compiled into the WIDE-block kernels only (28/32 frequencies per block: dense
+// spectra and sub-band sets, where nearly every line is far: config 3 kernel 1 -27 %, config 4 -30 %).
+// For the 14 HATPRO channels as ONE block only 23 of 65 lines are far and what the coarse grid saves
+// (7 % of the FP64 work) is lost again to the latency-bound hoists of the far pairs and to ptxas'
+// schedule of the near loops (measured 1.155 vs 1.140 ms per config-2 step), so the narrow kernels keep
+// the lean code.
+template <int FB>
+__host__ __device__ constexpr bool far_built() { return MWRT_ABS_FAR_BUILD != 0 && FB >= MWRT_ABS_FAR_MINFB; }
+// c_q = cos((2q+1) pi / (2 kNQ)) and 1 / prod_{q != n} (c_n - c_q)
+#if MWRT_ABS_NQ == 4
+static __device__ const double kChebNode[kNQ] = {0.9238795325112867, 0.38268343236508984, -0.3826834323650897,
+                                                 -0.9238795325112867};
+static __device__ const double kChebInvC[kNQ] = {0.7653668647301797, -1.8477590650225737, 1.8477590650225735,
+                                                 -0.7653668647301796};
+#elif MWRT_ABS_NQ == 6
+static __device__ const double kChebNode[kNQ] = {0.9659258262890683,   0.7071067811865476,  0.25881904510252074,
+                                                 -0.25881904510252063, -0.7071067811865475, -0.9659258262890682};
+static __device__ const double kChebInvC[kNQ] = {1.3803682405467776, -3.771236166328254, 5.151604406875032,
+                                                 -5.151604406875032, 3.771236166328254,  -1.3803682405467776};
+#else
+static __device__ const double kChebNode[kNQ] = {0.9807852804032304,  0.8314696123025452, 0.5555702330196023,
+                                                 0.19509032201612833, -0.1950903220161282, -0.555570233019602,
+                                                 -0.8314696123025453, -0.9807852804032304};
+static __device__ const double kChebInvC[kNQ] = {3.121445152258054,  -8.889123728313642,  13.30351379684073,
+                                                 -15.69256448645169, 15.692564486451694,  -13.303513796840717,
+                                                 8.889123728313624,  -3.1214451522580533};
+#endif
+
 __host__ __device__ inline int abs_smem_doubles(int nh, int no, int FB) {
   const int nop = (no + 1) & ~1;
-  // hrow, orow, fblk, fsq, dfm, dfp, dminh, dmino, then ints: hcls[nh], hord[nh], cnt[2], hchk[nh], ochk[nop]
-  const int n = nh * kHS + nop * kOS + 2 * FB + 2 * nh * FB + nh + nop + (3 * nh + nop + 2 + 1) / 2 + 1;
+  // hrow, orow, fblk, fsq, unode, mint, dfm, dfp, dminh, dmino, then ints: hcls[nh], hord[nh], cnt[4],
+  // hchk[nh], ochk[nop], oord[nop]
+  const int n = nh * kHS + nop * kOS + 2 * FB + kNQ + FB * kNQ + 2 * nh * FB + nh + nop +
+                (3 * nh + 2 * nop + 4 + 1) / 2 + 1;
   return (n + 1) & ~1;   // even: what follows (the fp32 tables) stays 16-byte aligned
 }
 
@@ -269,62 +324,51 @@ __device__ __forceinline__ void pair_accumulate_f32(float (&accf)[FB], const flo
   }
 }
 
+// doubles of one frequency block's scratch (everything behind the line tables, the fp32 tables included)
+__host__ __device__ inline int abs_block_doubles(int nh, int no, int FB, bool f32) {
+  const int nop = (no + 1) & ~1;
+  const int n = abs_smem_doubles(nh, no, FB) - (nh * kHS + nop * kOS) + (f32 ? (nh + nop) * ((FB + 3) & ~3) / 2 : 0);
+  return (n + 1) & ~1;
+}
+
+// Per-block scratch, ONE CTA per frequency block, once per (plan, knobs): the block's frequencies and
+// their squares, the Chebyshev nodes and Lagrange weights of the far-line grid, the exact detunings for
+// the slow paths, the line classes and processing orders, the fp32 detuning tables.  Kernel 1's CTAs
+// copy their block's record instead of rebuilding it (round 1 rebuilt it in each of 7 813 CTAs per
+// launch; the code of that prologue also swept the 32 KB instruction cache under the resident CTAs'
+// hot loops every time a CTA started -- measured: 5-12 % of kernel 1).
 template <int FB, bool F32>
-__global__ void __launch_bounds__(kAbsThreads, FB > 16 ? 3 : MWRT_ABS_MINB)
-k_absorption(const ModelDev m, const long long npts, const int L, const int F, const int nfb,
-             const double* __restrict__ p_in, const double* __restrict__ tk_in,
-             const double* __restrict__ e_in, const int e_is_rh, double* __restrict__ e_out,
-             double* __restrict__ rho_out, const double* __restrict__ frq,
-             double* __restrict__ awet, double* __restrict__ adry, int* __restrict__ status) {
+__global__ void __launch_bounds__(kAbsThreads)
+k_abs_blocks(const ModelDev m, const int F, const double* __restrict__ frq, const int far_on,
+             double* __restrict__ blocks, const int blk_stride) {
   extern __shared__ __align__(16) double smem[];
   const int nh = m.n_h2o, no = m.n_o2;
-  const int nop = (no + 1) & ~1;          // O2 lines padded to an even count (dummy: strength 0)
-  double* hrow = smem;                    // nh x kHS
-  double* orow = hrow + nh * kHS;         // nop x kOS
-  double* fblk = orow + nop * kOS;        // FB frequencies of this block
-  double* fsq = fblk + FB;                // FB: f_j^2
-  double* dfm = fsq + FB;                 // nh x FB: f_j - fl_i   (slow paths keep the oracle's rounding)
-  double* dfp = dfm + nh * FB;            // nh x FB: f_j + fl_i
-  double* dminh = dfp + nh * FB;          // nh: min_j |f_j - fl_i|
-  double* dmino = dminh + nh;             // nop: min_j |f_j - f_k|
-  int* hcls = reinterpret_cast<int*>(dmino + nop);   // nh: H2O line class w.r.t. the 750 GHz cutoff
-  int* hord = hcls + nh;                  // nh: processing order, all-in lines first
-  int* cnt = hord + nh;                   // [0] all-in lines, [1] lines that contribute at all
-  int* hchk = cnt + 2;                    // nh: can this line need a correction in this block at all?
-  int* ochk = hchk + nh;                  // nop: same for the O2 lines
-  // fp32 line-shape mode: (f_j^2 - f_line^2) rounded to fp32, nh rows then nop rows of FBP floats
-  // (rows padded to a multiple of four so that one LDS.128 brings four frequencies)
+  const int nop = (no + 1) & ~1;
+  double* hrow = smem;
+  double* orow = hrow + nh * kHS;
+  double* fblk = orow + nop * kOS;
+  double* fsq = fblk + FB;
+  double* unode = fsq + FB;
+  double* mint = unode + kNQ;
+  double* dfm = mint + FB * kNQ;
+  double* dfp = dfm + nh * FB;
+  double* dminh = dfp + nh * FB;
+  double* dmino = dminh + nh;
+  int* hcls = reinterpret_cast<int*>(dmino + nop);
+  int* hord = hcls + nh;
+  int* cnt = hord + nh;
+  int* hchk = cnt + 4;
+  int* ochk = hchk + nh;
+  int* oord = ochk + nop;
   constexpr int FBP = (FB + 3) & ~3;
   float* a32h = reinterpret_cast<float*>(smem + abs_smem_doubles(nh, no, FB));
   float* a32o = a32h + nh * FBP;
-  __shared__ double etab[kExpTabN];             // exp_tb / log_tb tables (mwrt_common.cuh)
-  __shared__ __align__(16) double ltab[128];
-  exp_tab_stage(etab);
-  log_tab_stage(ltab);
-  // line tables: a flat copy of the model's line-major rows (hrow and orow are contiguous)
+  (void)a32h; (void)a32o; (void)unode; (void)mint; (void)oord;
   for (int i = threadIdx.x; i < m.n_rows; i += blockDim.x) hrow[i] = m.rows[i];
-  // Work items = (frequency block, tile of kAbsThreads points); CTA b owns the contiguous item range
-  // [items*b/G, items*(b+1)/G) -- normally exactly one item (see launch_abs).
-  const long long ntiles = (npts + kAbsThreads - 1) / kAbsThreads;
-  const long long nitems_all = ntiles * nfb;
-  const long long it_begin = nitems_all * blockIdx.x / gridDim.x;
-  const long long it_end = nitems_all * (blockIdx.x + 1) / gridDim.x;
-  int cur_fb = -1;
-#pragma unroll 1
-  for (long long item = it_begin; item < it_end; ++item) {
-  const int fb = (int)(item / ntiles);
-  const long long tile = item - (long long)fb * ntiles;
-  const int f0 = fb * FB;
-  // the level-point's inputs are requested before the block scratch is built: their DRAM latency
-  // hides under the staging below
-  const long long ipt = tile * kAbsThreads + threadIdx.x;
-  const bool in_range = ipt < npts;
-  const double p_mb = in_range ? p_in[ipt] : 1000.0;
-  const double tk_raw = in_range ? tk_in[ipt] : 300.0;
-  double e_mb = in_range ? e_in[ipt] : 0.0;
-  if (fb != cur_fb) {
-    cur_fb = fb;
-    __syncthreads();   // everyone is done with the previous block's scratch (and with the tables' staging)
+  for (int i = threadIdx.x; i < blk_stride; i += blockDim.x) fblk[i] = 0.0;   // padding is defined
+  const int fb = blockIdx.x, f0 = fb * FB;
+  __syncthreads();
+  {
     if (threadIdx.x < FB) {
       int jf = f0 + threadIdx.x;
       const double f = frq[jf < F ? jf : F - 1];  // tail block: repeat the last frequency
@@ -368,33 +412,201 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
       if (w0_in && fl + hi < 749.0) cls = kAllIn;
       else if (w0_in && fl + lo > 751.0) cls = kWing1Out;
       else if (fl - hi > 751.0 || lo - fl > 751.0) cls = kAllOut;
-      hcls[i] = cls;
       // Corrections to the fast form are possible only for speed-dependent lines and for lines within
       // 1e-3*fl (+ the 1 GHz shift margin of the fast path) of a block frequency: decided here once
       // per CTA, so the per-thread tests run for those lines only (HATPRO: the 22 GHz line).
       const bool sd_cap = (m.h2o_sd != 0) && (hrow[i * kHS + MWRT_H2O_W2] != 0.0 || hrow[i * kHS + MWRT_H2O_W2S] != 0.0);
-      hchk[i] = (sd_cap || dmin < 1e-3 * fl + 1.0) ? 1 : 0;
+      const int chk = (sd_cap || dmin < 1e-3 * fl + 1.0) ? 1 : 0;
+      hchk[i] = chk;
+      // far line (see kNQ): all-in, never corrected, and its poles at least kFarRho block half-widths
+      // away from the block centre in u = f^2 whatever the shift (< 1 GHz) and width (w^2 < 37)
+      const double u_lo = lo * lo, u_hi = hi * hi, u0 = 0.5 * (u_lo + u_hi);
+      const double hh = fmax(0.5 * (u_hi - u_lo), 1e-3 * u0);
+      if (far_built<FB>() && far_on && !F32 && cls == kAllIn && !chk && fabs(fl * fl - u0) - 2.0 * fl - 37.0 >= kFarRho * hh)
+        cls = kFarIn;
+      hcls[i] = cls;
     }
     for (int i = threadIdx.x; i < nop; i += blockDim.x) {
       double fk = orow[i * kOS + MWRT_O2_F];
-      double dmin = fabs(fblk[0] - fk);
-      for (int j = 1; j < FB; ++j) dmin = fmin(dmin, fabs(fblk[j] - fk));
+      double dmin = fabs(fblk[0] - fk), lo = fblk[0], hi = fblk[0];
+      for (int j = 1; j < FB; ++j) {
+        dmin = fmin(dmin, fabs(fblk[j] - fk));
+        lo = fmin(lo, fblk[j]);
+        hi = fmax(hi, fblk[j]);
+      }
       dmino[i] = dmin;
       // a line can be 'narrow and very close' only within 1e-3*fk + its largest mixing shift
       // (|dnu0| + |dnu1| times a bound of 4 on den^2 and |th1| for atmospheric T, p) of a frequency
       const double shmax = 4.0 * (fabs(orow[i * kOS + MWRT_O2_DNU0]) + fabs(orow[i * kOS + MWRT_O2_DNU1])) + 1e-6;
-      ochk[i] = ((i == 0 && m.o2_sd118) || dmin < 1e-3 * fk + shmax) ? 1 : 0;
+      int chk = ((i == 0 && m.o2_sd118) || dmin < 1e-3 * fk + shmax) ? 1 : 0;
+      const double u_lo = lo * lo, u_hi = hi * hi, u0 = 0.5 * (u_lo + u_hi);
+      const double hh = fmax(0.5 * (u_hi - u_lo), 1e-3 * u0);
+      // far O2 line: marked 2 until the ordering below (the padding row beyond the model's lines stays near)
+      if (far_built<FB>() && far_on && !F32 && !chk && i < no && fabs(fk * fk - u0) - 2.0 * fk * shmax - 37.0 >= kFarRho * hh) chk = 2;
+      ochk[i] = chk;
+    }
+    // Chebyshev nodes of the block in u and the Lagrange weights from the nodes to the block's
+    // frequencies, in the normalised coordinate t = (u - u0)/h: L_n(t) = prod_{q != n} (t - c_q) / C_n with
+    // the node cosines c_q and the constants 1/C_n tabulated (no cos, no division, no extra barrier)
+    if (far_built<FB>() && !F32) {
+      double lo = fblk[0], hi = fblk[0];
+      for (int j = 1; j < FB; ++j) {
+        lo = fmin(lo, fblk[j]);
+        hi = fmax(hi, fblk[j]);
+      }
+      const double u_lo = lo * lo, u_hi = hi * hi, u0 = 0.5 * (u_lo + u_hi);
+      const double hh = fmax(0.5 * (u_hi - u_lo), 1e-3 * u0);
+      const double ihh = rcp_fast(hh);
+      if (threadIdx.x < kNQ) unode[threadIdx.x] = fma(hh, kChebNode[threadIdx.x], u0);
+      for (int i = threadIdx.x; i < FB * kNQ; i += blockDim.x) {
+        const int n = i % kNQ;
+        const double tt = (fsq[i / kNQ] - u0) * ihh;
+        double w = kChebInvC[n];
+#pragma unroll
+        for (int q = 0; q < kNQ; ++q) w *= (q != n) ? tt - kChebNode[q] : 1.0;
+        mint[i] = w;
+      }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int n = 0;
-      for (int i = 0; i < nh; ++i)
-        if (hcls[i] == kAllIn) hord[n++] = i;
-      cnt[0] = n;
-      for (int i = 0; i < nh; ++i)
-        if (hcls[i] != kAllIn && hcls[i] != kAllOut) hord[n++] = i;
-      cnt[1] = n;
+    // Processing orders, built with warp ballots (a serial loop by one thread would hold the whole CTA
+    // at the barrier below for ~100 dependent shared-memory round trips).
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    if ((threadIdx.x >> 5) == 0) {
+      // H2O: far lines (an even number, at most 64: an odd one out is simply treated as near), the
+      // other all-in lines, then the lines that need the exact loop; all-out lines are dropped
+      int nfar_tot = 0, nall_raw = 0;
+      for (int b = 0; b < nh; b += 32) {
+        const int cls = (b + lane < nh) ? hcls[b + lane] : kAllOut;
+        nfar_tot += __popc(__ballot_sync(0xffffffffu, cls == kFarIn));
+        nall_raw += __popc(__ballot_sync(0xffffffffu, cls == kAllIn));
+      }
+      const int nf = nfar_tot > 64 ? 64 : (nfar_tot & ~1);
+      const int n_in = nall_raw + nfar_tot;
+      int fb_ = 0, ab_ = 0, ob_ = 0;
+      for (int b = 0; b < nh; b += 32) {
+        const int i = b + lane;
+        const int cls = (i < nh) ? hcls[i] : kAllOut;
+        const bool isfar = cls == kFarIn;
+        const unsigned mf = __ballot_sync(0xffffffffu, isfar);
+        const int fpos = fb_ + __popc(mf & lt);
+        const bool kept = isfar && fpos < nf;
+        const bool isin = (cls == kAllIn) || (isfar && !kept);
+        const unsigned mi = __ballot_sync(0xffffffffu, isin);
+        const bool isoth = (cls == kWing1Out) || (cls == kMixed);
+        const unsigned mo = __ballot_sync(0xffffffffu, isoth);
+        if (kept) {
+          hord[fpos] = i;
+        } else if (isin) {
+          hord[nf + ab_ + __popc(mi & lt)] = i;
+          if (isfar) hcls[i] = kAllIn;
+        } else if (isoth) {
+          hord[n_in + ob_ + __popc(mo & lt)] = i;
+        }
+        fb_ += __popc(mf);
+        ab_ += __popc(mi);
+        ob_ += __popc(mo);
+      }
+      if (lane == 0) {
+        cnt[2] = nf;
+        cnt[0] = n_in;
+        cnt[1] = n_in + ob_;
+      }
+    } else if ((threadIdx.x >> 5) == 1) {
+      // O2: far lines (even count) first, then the rest in table order (the padding row last)
+      int nfar_tot = 0;
+      for (int b = 0; b < nop; b += 32)
+        nfar_tot += __popc(__ballot_sync(0xffffffffu, (b + lane < nop) && ochk[b + lane] == 2));
+      const int nf = nfar_tot & ~1;
+      int fb_ = 0;
+      for (int b = 0; b < nop; b += 32) {
+        const int i = b + lane;
+        const bool isfar = (i < nop) && ochk[i] == 2;
+        const unsigned mf = __ballot_sync(0xffffffffu, isfar);
+        const int fpos = fb_ + __popc(mf & lt);   // far lines before line i
+        if (i < nop) {
+          if (isfar && fpos < nf) {
+            oord[fpos] = i;
+          } else {
+            oord[nf + i - (fpos < nf ? fpos : nf)] = i;   // i lines before, min(fpos, nf) of them kept far
+            if (isfar) ochk[i] = 0;
+          }
+        }
+        fb_ += __popc(mf);
+      }
+      if (lane == 0) cnt[3] = nf;
     }
+    __syncthreads();
+  }
+  double* dst = blocks + (size_t)fb * blk_stride;
+  for (int i = threadIdx.x; i < blk_stride; i += blockDim.x) dst[i] = fblk[i];
+}
+
+template <int FB, bool F32>
+__global__ void __launch_bounds__(kAbsThreads, FB > 16 ? 3 : MWRT_ABS_MINB)
+k_absorption(const ModelDev m, const long long npts, const int L, const int F, const int nfb,
+             const double* __restrict__ p_in, const double* __restrict__ tk_in,
+             const double* __restrict__ e_in, const int e_is_rh, double* __restrict__ e_out,
+             double* __restrict__ rho_out, const double* __restrict__ frq,
+             double* __restrict__ awet, double* __restrict__ adry, int* __restrict__ status,
+             const double* __restrict__ blocks, const int blk_stride) {
+  extern __shared__ __align__(16) double smem[];
+  const int nh = m.n_h2o, no = m.n_o2;
+  const int nop = (no + 1) & ~1;          // O2 lines padded to an even count (dummy: strength 0)
+  double* hrow = smem;                    // nh x kHS
+  double* orow = hrow + nh * kHS;         // nop x kOS
+  double* fblk = orow + nop * kOS;        // FB frequencies of this block
+  double* fsq = fblk + FB;                // FB: f_j^2
+  double* unode = fsq + FB;               // kNQ: Chebyshev nodes of the block in u = f^2 (far lines)
+  double* mint = unode + kNQ;             // FB x kNQ: Lagrange weights node -> frequency
+  double* dfm = mint + FB * kNQ;          // nh x FB: f_j - fl_i   (slow paths keep the oracle's rounding)
+  double* dfp = dfm + nh * FB;            // nh x FB: f_j + fl_i
+  double* dminh = dfp + nh * FB;          // nh: min_j |f_j - fl_i|
+  double* dmino = dminh + nh;             // nop: min_j |f_j - f_k|
+  int* hcls = reinterpret_cast<int*>(dmino + nop);   // nh: H2O line class w.r.t. the 750 GHz cutoff
+  int* hord = hcls + nh;                  // nh: processing order, all-in lines first
+  int* cnt = hord + nh;                   // [0] all-in lines, [1] lines that contribute at all,
+                                          // [2] far H2O lines (even, first in hord), [3] far O2 lines (even)
+  int* hchk = cnt + 4;                    // nh: can this line need a correction in this block at all?
+  int* ochk = hchk + nh;                  // nop: same for the O2 lines
+  int* oord = ochk + nop;                 // nop: O2 processing order, far lines first
+  // fp32 line-shape mode: (f_j^2 - f_line^2) rounded to fp32, nh rows then nop rows of FBP floats
+  // (rows padded to a multiple of four so that one LDS.128 brings four frequencies)
+  constexpr int FBP = (FB + 3) & ~3;
+  float* a32h = reinterpret_cast<float*>(smem + abs_smem_doubles(nh, no, FB));
+  float* a32o = a32h + nh * FBP;
+  __shared__ double etab[kExpTabN];             // exp_tb / log_tb tables (mwrt_common.cuh)
+  __shared__ __align__(16) double ltab[128];
+  exp_tab_stage(etab);
+  log_tab_stage(ltab);
+  // line tables: a flat copy of the model's line-major rows (hrow and orow are contiguous)
+  for (int i = threadIdx.x; i < m.n_rows; i += blockDim.x) hrow[i] = m.rows[i];
+  // Work items = (frequency block, tile of kAbsThreads points); CTA b owns the contiguous item range
+  // [items*b/G, items*(b+1)/G) -- normally exactly one item (see launch_abs).
+  const long long ntiles = (npts + kAbsThreads - 1) / kAbsThreads;
+  const long long nitems_all = ntiles * nfb;
+  const long long it_begin = nitems_all * blockIdx.x / gridDim.x;
+  const long long it_end = nitems_all * (blockIdx.x + 1) / gridDim.x;
+  int cur_fb = -1;
+#pragma unroll 1
+  for (long long item = it_begin; item < it_end; ++item) {
+  const int fb = (int)(item / ntiles);
+  const long long tile = item - (long long)fb * ntiles;
+  const int f0 = fb * FB;
+  // the level-point's inputs are requested before the block scratch is built: their DRAM latency
+  // hides under the staging below
+  const long long ipt = tile * kAbsThreads + threadIdx.x;
+  const bool in_range = ipt < npts;
+  const double p_mb = in_range ? p_in[ipt] : 1000.0;
+  const double tk_raw = in_range ? tk_in[ipt] : 300.0;
+  double e_mb = in_range ? e_in[ipt] : 0.0;
+  if (fb != cur_fb) {
+    cur_fb = fb;
+    __syncthreads();   // everyone is done with the previous block's scratch
+    // the block's scratch, built once per launch configuration by k_abs_blocks: a flat 16-byte copy
+    const double2* src = reinterpret_cast<const double2*>(blocks + (size_t)fb * blk_stride);
+    double2* dst = reinterpret_cast<double2*>(fblk);
+    for (int i = threadIdx.x; i < (blk_stride >> 1); i += blockDim.x) dst[i] = src[i];
     __syncthreads();
   }
   if (in_range) {
@@ -486,8 +698,6 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
       return sd_any || narrow;
     };
 
-#pragma unroll
-    for (int j = 0; j < FB; ++j) acc[j] = 0.0;
     if constexpr (F32) {
 #pragma unroll
       for (int j = 0; j < FB; ++j) accf[j] = 0.0f;
@@ -496,12 +706,63 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
     const int n_in = cnt[0], n_act = cnt[1];
     const int npairs = (n_in + 1) >> 1;
     const int nitems = npairs + (n_act - n_in);
+    // far pairs first (see kNQ): the pair loop at the kNQ nodes of the block, then one interpolation to
+    // the block's frequencies, which initialises the running sums
+    const int nfar = far_built<FB>() ? cnt[2] >> 1 : 0;
+    unsigned far_bad = 0;   // far pairs whose pressure shift broke the 1 GHz margin: exact loop below
+    if (far_built<FB>() && !F32 && nfar > 0) {
+      double accn[kNQ];
+#pragma unroll
+      for (int n = 0; n < kNQ; ++n) accn[n] = 0.0;
+#pragma unroll 1
+      for (int it = 0; it < nfar; ++it) {
+        const double* Ra = hrow + hord[2 * it] * kHS;
+        const double* Rb = hrow + hord[2 * it + 1] * kHS;
+        double ea[6], ev[6];
+        ea[0] = Ra[MWRT_H2O_X] * tiln;
+        ea[1] = Ra[MWRT_H2O_XS] * tiln;
+        ea[2] = fma(2.5, tiln, Ra[MWRT_H2O_B2] * omti);
+        ea[3] = Rb[MWRT_H2O_X] * tiln;
+        ea[4] = Rb[MWRT_H2O_XS] * tiln;
+        ea[5] = fma(2.5, tiln, Rb[MWRT_H2O_B2] * omti);
+        exp_tb_vec<6>(ea, ev, etab);
+        const H2OLine ga = line_state(Ra, ev[0], ev[1], ev[2]);
+        const H2OLine gb = line_state(Rb, ev[3], ev[4], ev[5]);
+        if ((fabs(ga.shift) < 1.0) && (fabs(gb.shift) < 1.0)) {
+          basesum += 2.0 * ga.sp * ga.base + 2.0 * gb.sp * gb.base;
+          const PairHot h{ga.c3, ga.c4, ga.n1, ga.n0, gb.c3, gb.c4, gb.n1, gb.n0};
+          pair_accumulate<kNQ>(accn, reinterpret_cast<const double2*>(unode), h);
+        } else {
+          far_bad |= 1u << it;
+        }
+      }
+      const double2* mi2 = reinterpret_cast<const double2*>(mint);
+#pragma unroll
+      for (int j = 0; j < FB; ++j) {
+        double a = 0.0;
+#pragma unroll
+        for (int n = 0; n < kNQ; n += 2) {
+          const double2 w = mi2[(j * kNQ + n) >> 1];
+          a = fma(w.x, accn[n], a);
+          a = fma(w.y, accn[n + 1], a);
+        }
+        acc[j] = a;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < FB; ++j) acc[j] = 0.0;
+    }
     // work items: pairs of all-in lines (fast pair form + corrections), then the remaining lines one
     // at a time through the exact per-wing loop
 #pragma unroll 1
-    for (int it = 0; it < nitems; ++it) {
+    for (int it = far_bad ? 0 : nfar; it < nitems; ++it) {
       int ia, ib, ma = kSlowNone, mb = kSlowNone;
-      if (it < npairs) {
+      if (it < nfar) {
+        if (!((far_bad >> it) & 1u)) continue;
+        ia = hord[2 * it];
+        ib = hord[2 * it + 1];
+        ma = mb = kSlowExact;
+      } else if (it < npairs) {
         const int q = 2 * it;
         const bool has_b = q + 1 < n_in;
         ia = hord[q];
@@ -700,12 +961,94 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
       return o;
     };
 
-#pragma unroll
-    for (int j = 0; j < FB; ++j) acc[j] = 0.0;
     if constexpr (F32) {
 #pragma unroll
       for (int j = 0; j < FB; ++j) accf[j] = 0.0f;
     }
+    // Lines are taken in the block's order `oord` (far lines first, then table order), two at a time.
+    // hoisted state of the pair at positions (2q, 2q+1) of that order, software-pipelined loops below
+    struct O2Pair { double c3a, c4a, n1a, n0a, ba, c3b, c4b, n1b, n0b, bb; };
+    auto pair_hot = [&](int q) {
+      const int ka = far_built<FB>() ? oord[2 * q] : 2 * q, kb = far_built<FB>() ? oord[2 * q + 1] : 2 * q + 1;
+      double ea[2], ev[2];
+      ea[0] = -orow[ka * kOS + MWRT_O2_BE] * th1;
+      ea[1] = -orow[kb * kOS + MWRT_O2_BE] * th1;
+      exp_tb_vec<2>(ea, ev, etab);
+      const O2Line a = hoist(ka, ev[0]), c = hoist(kb, ev[1]);
+      return O2Pair{a.c3, a.c4, a.n1, a.n0, a.b32, c.c3, c.c4, c.n1, c.n0, c.b32};
+    };
+    // far pairs (see kNQ): pair loop at the block's kNQ nodes, pipelined like the narrow-block loop
+    // below (the hoist of the next pair in the same basic block), then ONE interpolation to the block's
+    // frequencies, which initialises the running sums
+    const int nqf = far_built<FB>() ? cnt[3] >> 1 : 0, nqp = nop >> 1;
+    if (far_built<FB>() && !F32 && nqf > 0) {
+      double accn[kNQ];
+#pragma unroll
+      for (int n = 0; n < kNQ; ++n) accn[n] = 0.0;
+      O2Pair cur = pair_hot(0);
+#pragma unroll 1
+      for (int q = 0; q < nqf; ++q) {
+        const O2Pair nxt = pair_hot(q + 1 < nqf ? q + 1 : q);   // (last pass: recomputed and dropped)
+        const PairHot h{cur.c3a, cur.c4a, cur.n1a, cur.n0a, cur.c3b, cur.c4b, cur.n1b, cur.n0b};
+        pair_accumulate<kNQ>(accn, reinterpret_cast<const double2*>(unode), h);
+        cur = nxt;
+      }
+      const double2* mi2 = reinterpret_cast<const double2*>(mint);
+#pragma unroll
+      for (int j = 0; j < FB; ++j) {
+        double a = 0.0;
+#pragma unroll
+        for (int n = 0; n < kNQ; n += 2) {
+          const double2 w = mi2[(j * kNQ + n) >> 1];
+          a = fma(w.x, accn[n], a);
+          a = fma(w.y, accn[n + 1], a);
+        }
+        acc[j] = a;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < FB; ++j) acc[j] = 0.0;
+    }
+    // rare: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency -- what the
+    // oracle adds minus what the fast form contributed (lines ka, kb of a near pair; full state recomputed)
+    auto o2_corrections = [&](int ka, int kb) {
+      const double expa = exp_tb_(-orow[ka * kOS + MWRT_O2_BE] * th1);
+      const double expb = exp_tb_(-orow[kb * kOS + MWRT_O2_BE] * th1);
+      const O2Line oa = hoist(ka, expa);
+      const O2Line ob = hoist(kb, expb);
+      const double fka = orow[ka * kOS + MWRT_O2_F], fkb = orow[kb * kOS + MWRT_O2_F];
+      const bool sda = m.o2_sd118 && ka == 0 && (f_lo - oa.fcen < 10.0 * oa.df) &&
+                       (oa.fcen - f_hi < 10.0 * oa.df);
+      const bool sdb = m.o2_sd118 && kb == 0 && (f_lo - ob.fcen < 10.0 * ob.df) &&
+                       (ob.fcen - f_hi < 10.0 * ob.df);
+      const bool nwa = (oa.df < 1e-3 * fka) && (dmino[ka] - fabs(oa.fcen - fka) < 1e-3 * fka);
+      const bool nwb = (ob.df < 1e-3 * fkb) && (dmino[kb] - fabs(ob.fcen - fkb) < 1e-3 * fkb);
+      const int ca = (sda || nwa) ? 1 : 0, cb = (sdb || nwb) ? 1 : 0;
+      if (!(ca | cb)) return;
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {
+        if (!(s ? cb : ca)) continue;
+        const int kk = s ? kb : ka;
+        const bool sd = s ? sdb : sda;
+        const O2Line g = hoist(kk, s ? expb : expa);   // full line state, recomputed
+#pragma unroll 1
+        for (int j = 0; j < FB; ++j) {
+          const double d1 = fblk[j] - g.fcen;
+          const double d2 = fblk[j] + g.fcen;
+          double sf1;
+          if (sd && fabs(d1) < 10.0 * g.df)
+            sf1 = o2_sd118_sf1(g.df, d1, g.y);
+          else
+            sf1 = div_fast(g.df * g.gfac + d1 * g.y, fma(d1, d1, g.df2));
+          const double sf2 = div_fast(g.df * g.gfac - d2 * g.y, fma(d2, d2, g.df2));
+          const double vv = fsq[j] - g.c3;
+          const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
+          tmp[j] = fma(g.sp, sf1 + sf2, -fast);
+        }
+#pragma unroll
+        for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
+      }
+    };
     // Narrow blocks (FB <= 16): SOFTWARE PIPELINE over the line pairs -- the hoisted parameters of pair
     // k+1 (two strength exps and ~45 dependent FP64 operations: a latency-bound chain) are computed in
     // the same basic block as the frequency loop of pair k (FB independent chains: throughput-bound), so
@@ -714,130 +1057,61 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
     // (profiles/r02j_variants.txt): 0.804 -> 0.776 ms for config 2, bit-identical; with 28/32-wide blocks
     // the loop already hides what there is to hide and the extra live registers cost 5-6 %, and the same
     // pipeline over the H2O pairs (six exps and two line states in flight) is slower everywhere (0.87 ms)
-    // -- both keep the plain form.  The two forms are kept as two verbatim code paths (no shared
-    // helpers): sharing them through lambdas changed the register allocation of BOTH and lost the gain.
+    // -- both keep the plain form.
     constexpr bool kO2Pipe = (FB <= 16) && (MWRT_ABS_O2_PIPELINE != 0);
     if constexpr (kO2Pipe) {
-      struct O2Pair { double c3a, c4a, n1a, n0a, ba, c3b, c4b, n1b, n0b, bb; };
-      auto pair_hot = [&](int k) {
-        double ea[2], ev[2];
-        ea[0] = -orow[k * kOS + MWRT_O2_BE] * th1;
-        ea[1] = -orow[(k + 1) * kOS + MWRT_O2_BE] * th1;
-        exp_tb_vec<2>(ea, ev, etab);
-        const O2Line a = hoist(k, ev[0]), c = hoist(k + 1, ev[1]);
-        return O2Pair{a.c3, a.c4, a.n1, a.n0, a.b32, c.c3, c.c4, c.n1, c.n0, c.b32};
-      };
-      O2Pair cur = pair_hot(0);
+      if (nqf < nqp) {
+      O2Pair cur = pair_hot(nqf);
 #pragma unroll 1
-      for (int k = 0; k < nop; k += 2) {
-        const O2Pair nxt = pair_hot(k + 2 < nop ? k + 2 : k);   // (last pass: recomputed and dropped)
+      for (int q = nqf; q < nqp; ++q) {
+        const O2Pair nxt = pair_hot(q + 1 < nqp ? q + 1 : q);   // (last pass: recomputed and dropped)
+        const int ka = far_built<FB>() ? oord[2 * q] : 2 * q, kb = far_built<FB>() ? oord[2 * q + 1] : 2 * q + 1;
         if constexpr (F32) {
           const PairHotF h{(float)cur.ba, (float)cur.c4a, (float)(cur.n1a * kF32Scale), (float)(cur.n0a * kF32Scale),
                            (float)cur.bb, (float)cur.c4b, (float)(cur.n1b * kF32Scale), (float)(cur.n0b * kF32Scale)};
-          pair_accumulate_f32<FB>(accf, a32o + k * FBP, a32o + (k + 1) * FBP, h);
+          pair_accumulate_f32<FB>(accf, a32o + ka * FBP, a32o + kb * FBP, h);
         } else {
           const PairHot h{cur.c3a, cur.c4a, cur.n1a, cur.n0a, cur.c3b, cur.c4b, cur.n1b, cur.n0b};
           pair_accumulate<FB>(acc, fsq2, h);
         }
         cur = nxt;
-        // rare: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency
-        if (!(ochk[k] | ochk[k + 1])) continue;   // uniform, decided per CTA
-        const double expa = exp_tb_(-orow[k * kOS + MWRT_O2_BE] * th1);
-        const double expb = exp_tb_(-orow[(k + 1) * kOS + MWRT_O2_BE] * th1);
-        const O2Line oa = hoist(k, expa);
-        const O2Line ob = hoist(k + 1, expb);
-        const double fka = orow[k * kOS + MWRT_O2_F], fkb = orow[(k + 1) * kOS + MWRT_O2_F];
-        const bool sda = m.o2_sd118 && k == 0 && (f_lo - oa.fcen < 10.0 * oa.df) &&
-                         (oa.fcen - f_hi < 10.0 * oa.df);
-        const bool nwa = (oa.df < 1e-3 * fka) && (dmino[k] - fabs(oa.fcen - fka) < 1e-3 * fka);
-        const bool nwb = (ob.df < 1e-3 * fkb) && (dmino[k + 1] - fabs(ob.fcen - fkb) < 1e-3 * fkb);
-        const int ca = (sda || nwa) ? 1 : 0, cb = nwb ? 1 : 0;
-        if (!(ca | cb)) continue;
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-          if (!(s ? cb : ca)) continue;
-          const int kk = k + s;
-          const bool sd = sda && s == 0;
-          const O2Line g = hoist(kk, s ? expb : expa);   // full line state, recomputed
-#pragma unroll 1
-          for (int j = 0; j < FB; ++j) {
-            const double d1 = fblk[j] - g.fcen;
-            const double d2 = fblk[j] + g.fcen;
-            double sf1;
-            if (sd && fabs(d1) < 10.0 * g.df)
-              sf1 = o2_sd118_sf1(g.df, d1, g.y);
-            else
-              sf1 = div_fast(g.df * g.gfac + d1 * g.y, fma(d1, d1, g.df2));
-            const double sf2 = div_fast(g.df * g.gfac - d2 * g.y, fma(d2, d2, g.df2));
-            const double vv = fsq[j] - g.c3;
-            const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
-            tmp[j] = fma(g.sp, sf1 + sf2, -fast);
-          }
-#pragma unroll
-          for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
-        }
+        if (!(ochk[ka] | ochk[kb])) continue;   // uniform, decided per CTA
+        o2_corrections(ka, kb);
       }   // pairs
+      }
     } else {
     // Wide blocks: the line strengths need one exp each.  They are evaluated G at a time, interleaved
     // (exp_tb_vec), so the FP64 pipe sees G independent chains; the values are handed to the pair
     // loop by rotating a small register array (no dynamic indexing).
     constexpr int G = 6;
+    const int n0 = 2 * nqf;
 #pragma unroll 1
-    for (int k0 = 0; k0 < nop; k0 += G) {
+    for (int k0 = n0; k0 < nop; k0 += G) {
       double ea[G], ev[G];
 #pragma unroll
       for (int g = 0; g < G; ++g)
-        ea[g] = -orow[(k0 + g < nop ? k0 + g : nop - 1) * kOS + MWRT_O2_BE] * th1;
+        ea[g] = -orow[(far_built<FB>() ? oord[k0 + g < nop ? k0 + g : nop - 1] : (k0 + g < nop ? k0 + g : nop - 1)) * kOS + MWRT_O2_BE] * th1;
       exp_tb_vec<G>(ea, ev, etab);
 #pragma unroll 1
       for (int gi = 0; gi < G; gi += 2) {
         const int k = k0 + gi;
         if (k >= nop) break;
+        const int ka = far_built<FB>() ? oord[k] : k, kb = far_built<FB>() ? oord[k + 1] : k + 1;
         const double expa = ev[0], expb = ev[1];
 #pragma unroll
         for (int q = 0; q + 2 < G; ++q) ev[q] = ev[q + 2];
-        const O2Line oa = hoist(k, expa);
-        const O2Line ob = hoist(k + 1, expb);
+        const O2Line oa = hoist(ka, expa);
+        const O2Line ob = hoist(kb, expb);
         if constexpr (F32) {
           const PairHotF h{(float)oa.b32, (float)oa.c4, (float)(oa.n1 * kF32Scale), (float)(oa.n0 * kF32Scale),
                            (float)ob.b32, (float)ob.c4, (float)(ob.n1 * kF32Scale), (float)(ob.n0 * kF32Scale)};
-          pair_accumulate_f32<FB>(accf, a32o + k * FBP, a32o + (k + 1) * FBP, h);
+          pair_accumulate_f32<FB>(accf, a32o + ka * FBP, a32o + kb * FBP, h);
         } else {
         const PairHot h{oa.c3, oa.c4, oa.n1, oa.n0, ob.c3, ob.c4, ob.n1, ob.n0};
         pair_accumulate<FB>(acc, fsq2, h);
         }
-        // rare: speed-dependent 118.75 GHz line, or a very narrow line very close to a frequency
-        if (!(ochk[k] | ochk[k + 1])) continue;   // uniform, decided per CTA
-        const double fka = orow[k * kOS + MWRT_O2_F], fkb = orow[(k + 1) * kOS + MWRT_O2_F];
-        const bool sda = m.o2_sd118 && k == 0 && (f_lo - oa.fcen < 10.0 * oa.df) &&
-                         (oa.fcen - f_hi < 10.0 * oa.df);
-        const bool nwa = (oa.df < 1e-3 * fka) && (dmino[k] - fabs(oa.fcen - fka) < 1e-3 * fka);
-        const bool nwb = (ob.df < 1e-3 * fkb) && (dmino[k + 1] - fabs(ob.fcen - fkb) < 1e-3 * fkb);
-        const int ca = (sda || nwa) ? 1 : 0, cb = nwb ? 1 : 0;
-        if (!(ca | cb)) continue;
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-          if (!(s ? cb : ca)) continue;
-          const int kk = k + s;
-          const bool sd = sda && s == 0;
-          const O2Line g = hoist(kk, s ? expb : expa);   // full line state, recomputed
-#pragma unroll 1
-          for (int j = 0; j < FB; ++j) {
-            const double d1 = fblk[j] - g.fcen;
-            const double d2 = fblk[j] + g.fcen;
-            double sf1;
-            if (sd && fabs(d1) < 10.0 * g.df)
-              sf1 = o2_sd118_sf1(g.df, d1, g.y);
-            else
-              sf1 = div_fast(g.df * g.gfac + d1 * g.y, fma(d1, d1, g.df2));
-            const double sf2 = div_fast(g.df * g.gfac - d2 * g.y, fma(d2, d2, g.df2));
-            const double vv = fsq[j] - g.c3;
-            const double fast = fma(g.n1, vv, g.n0) * rcp_fast(fma(vv, vv, g.c4));
-            tmp[j] = fma(g.sp, sf1 + sf2, -fast);
-          }
-#pragma unroll
-          for (int j = 0; j < FB; ++j) acc[j] += tmp[j];
-        }
+        if (!(ochk[ka] | ochk[kb])) continue;   // uniform, decided per CTA
+        o2_corrections(ka, kb);
       }   // pairs of the group
     }     // groups
     }
@@ -868,32 +1142,105 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
   }   // work items
 }
 
+// Stream-ordered scratch for the plan-less stage entry point: a private pool that keeps its memory
+// between calls (the default pool returns it at every synchronisation, 0.2 ms per call measured)
+static cudaError_t abs_scratch_alloc(double** out, size_t bytes, cudaStream_t st) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaMallocAsync(out, bytes, st);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pools[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      e = cudaMemPoolCreate(&pools[dev], &props);
+      if (e != cudaSuccess) return e;
+      unsigned long long keep = ~0ull;
+      e = cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+      if (e != cudaSuccess) return e;
+    }
+  }
+  return cudaMallocFromPoolAsync(out, bytes, pools[dev], st);
+}
+
 template <int FB, bool F32>
 static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, const double* tk,
                       const double* e, int e_is_rh, double* e_out, double* rho_out, const double* frq,
-                      double* awet, double* adry, int* status, cudaStream_t st) {
+                      double* awet, double* adry, int* status, AbsBlocks* cache, cudaStream_t st) {
+  // MWRT_ABS_FAR=0 evaluates every line at every frequency (the round-1 form); read per call like
+  // MWRT_ABS_WIDE so that tests compare the two paths in one process
+  const char* fenv = getenv("MWRT_ABS_FAR");
+  const int far_on = fenv ? atoi(fenv) : 1;
   const long long npts = (long long)P * L;
   const int nfb = (F + FB - 1) / FB;
   const long long items = ((npts + kAbsThreads - 1) / kAbsThreads) * nfb;
   // One work item per CTA whenever the grid allows it.  Measured on B200 (config 2): a persistent grid
-  // (one resident wave looping over items) is 6-10 % SLOWER -- the per-CTA staging is LSU/ALU work that
-  // hides under other CTAs' FP64 work anyway, while a static split quantises to whole items per CTA
-  // and lets the warps of a CTA drift apart (more instruction-cache misses).  The item loop in the
-  // kernel only matters beyond 2^31-1 items.
+  // (one resident wave looping over items) is 6-10 % SLOWER -- a static split quantises to whole items
+  // per CTA and lets the warps of a CTA drift apart (more instruction-cache misses).  The item loop in
+  // the kernel only matters beyond 2^31-1 items.
   const unsigned grid = (unsigned)(items < 0x7fffffffLL ? items : 0x7fffffffLL);
   const int nop = (m.n_o2 + 1) & ~1;
   size_t smem = sizeof(double) * (size_t)abs_smem_doubles(m.n_h2o, m.n_o2, FB) +
                 (F32 ? sizeof(float) * (size_t)(m.n_h2o + nop) * ((FB + 3) & ~3) : 0);
+  // The shared-memory carve-out is asked for explicitly: 4 (3 for wide blocks) resident CTAs need a
+  // little more than 64 KiB since the far-line tables were added.
+  {
+    static const cudaError_t carve = [] {
+      const char* cenv = getenv("MWRT_ABS_CARVEOUT");   // percent of the SM's shared memory; -1 = driver default
+      const int pct = cenv ? atoi(cenv) : 50;
+      return pct < 0 ? cudaSuccess
+                     : cudaFuncSetAttribute(k_absorption<FB, F32>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }();
+    if (carve != cudaSuccess) return fail_arg(MWRT_E_STATE, "k_absorption: cannot set the shared-memory carve-out");
+  }
   if (smem > 48 * 1024) {
     static bool once = [] {
       return cudaFuncSetAttribute(k_absorption<FB, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  96 * 1024) == cudaSuccess &&
+             cudaFuncSetAttribute(k_abs_blocks<FB, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   96 * 1024) == cudaSuccess;
     }();
     if (!once) return fail_arg(MWRT_E_STATE, "k_absorption: cannot raise the dynamic shared-memory limit");
   }
+  // Per-block scratch: built by k_abs_blocks.  A plan keeps it (`cache`): rebuilt only when the block
+  // width, precision, far-line switch or frequency list changed, then the stream is synchronised ONCE so
+  // that the plan's other streams may read it.  The stage entry point (no plan) builds it per call into
+  // a stream-ordered allocation.
+  const int stride = abs_block_doubles(m.n_h2o, m.n_o2, FB, F32);
+  const size_t need = (size_t)nfb * stride;
+  double* blocks = nullptr;
+  if (cache) {
+    const bool hit = cache->buf && cache->fb == FB && cache->f32 == (int)F32 && cache->far == far_on &&
+                     cache->F == F && cache->frq == frq;
+    if (!hit) {
+      MWRT_CUDA_OK(cudaDeviceSynchronize());   // rare path: earlier launches on other streams may still read it
+      if (cache->cap < need) {
+        if (cache->buf) MWRT_CUDA_OK(cudaFree(cache->buf));   // (synchronises the device: nobody reads it any more)
+        cache->buf = nullptr;
+        cache->cap = 0;
+        MWRT_CUDA_OK(cudaMalloc(&cache->buf, sizeof(double) * need));
+        cache->cap = need;
+      }
+      k_abs_blocks<FB, F32><<<nfb, kAbsThreads, smem, st>>>(m, F, frq, far_on, cache->buf, stride);
+      MWRT_CUDA_OK(cudaGetLastError());
+      MWRT_CUDA_OK(cudaStreamSynchronize(st));
+      cache->fb = FB; cache->f32 = (int)F32; cache->far = far_on; cache->F = F; cache->frq = frq;
+    }
+    blocks = cache->buf;
+  } else {
+    MWRT_CUDA_OK(abs_scratch_alloc(&blocks, sizeof(double) * need, st));
+    k_abs_blocks<FB, F32><<<nfb, kAbsThreads, smem, st>>>(m, F, frq, far_on, blocks, stride);
+    MWRT_CUDA_OK(cudaGetLastError());
+  }
   k_absorption<FB, F32><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, nfb, p, tk, e, e_is_rh, e_out,
-                                                         rho_out, frq, awet, adry, status);
+                                                         rho_out, frq, awet, adry, status, blocks, stride);
   MWRT_CUDA_OK(cudaGetLastError());
+  if (!cache) MWRT_CUDA_OK(cudaFreeAsync(blocks, st));
   return 0;
 }
 
@@ -901,8 +1248,8 @@ static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, c
 // long lists take wide blocks.  f32ls selects the fp32 line-shape instantiation.
 int absorption_launch(const ModelDev& m, int P, int L, int F, const double* p, const double* tk,
                       const double* e, int e_is_rh, double* e_out, double* rho_out, const double* frq,
-                      double* awet, double* adry, int* status, int f32ls, cudaStream_t st) {
-#define MWRT_ABS_ARGS m, P, L, F, p, tk, e, e_is_rh, e_out, rho_out, frq, awet, adry, status, st
+                      double* awet, double* adry, int* status, int f32ls, AbsBlocks* cache, cudaStream_t st) {
+#define MWRT_ABS_ARGS m, P, L, F, p, tk, e, e_is_rh, e_out, rho_out, frq, awet, adry, status, cache, st
 #define MWRT_ABS_GO(FB_) return f32ls ? launch_abs<FB_, true>(MWRT_ABS_ARGS) : launch_abs<FB_, false>(MWRT_ABS_ARGS)
   // Block width for long frequency lists (MWRT_ABS_WIDE=0 switches the 28/32-wide blocks off): the
   // hoisted line parameters (40 % of a 14-wide block's FP64 work) are shared by every frequency of the

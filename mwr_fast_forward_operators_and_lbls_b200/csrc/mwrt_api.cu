@@ -33,7 +33,7 @@ int fail_arg(int code, const char* what) {
 // launchers defined in mwrt_absorption.cu / mwrt_rte.cu
 int absorption_launch(const ModelDev& m, int P, int L, int F, const double* p, const double* tk,
                       const double* e, int e_is_rh, double* e_out, double* rho_out, const double* frq,
-                      double* awet, double* adry, int* status, int f32ls, cudaStream_t st);
+                      double* awet, double* adry, int* status, int f32ls, AbsBlocks* cache, cudaStream_t st);
 int cloud_abs_launch(const ModelDev& m, int P, int L, int F, const double* tk, const double* denliq,
                      const double* denice, const double* frq, double* aliq, double* aice, cudaStream_t st);
 int vapor_launch(long long n, const double* tk, const double* rh, double* e, double* rho, cudaStream_t st);
@@ -90,6 +90,7 @@ struct mwrt_plan {
   int C = 0, S = 0;            // band-pass (C == 0: off)
   int bp_cpb = 0;              // > 0: the band-pass is reduced inside kernel 3, this many channels per CTA
   int f32ls = 0;               // fp32 line-shape mode of kernel 1 (mwrt_plan_set_precision)
+  AbsBlocks abs_blocks{};      // kernel 1's per-frequency-block scratch, built on first use
   double* d_frq = nullptr;
   double* d_angles = nullptr;
   double* d_amass = nullptr;   // (A,) 1/sin(elevation), computed on the host like PyRTlib does
@@ -248,7 +249,7 @@ static int absorption_stage(const mwrt_model* m, int P, int L, int F, const doub
   if (!m || P <= 0 || L <= 0 || F <= 0 || !p || !tk || !e || !frq || !awet || !adry)
     return fail_arg(MWRT_E_ARG, "mwrt_absorption: bad argument");
   int rc = absorption_launch(m->dev, P, L, F, p, tk, e, 0, nullptr, nullptr, frq, awet, adry, status, f32ls,
-                             (cudaStream_t)stream);
+                             /*cache=*/nullptr, (cudaStream_t)stream);
   if (rc) return rc;
   if (aliq || aice)   // RTEquation.cloudy_absorption, elementwise (the fused path evaluates it inside kernel 3)
     rc = cloud_abs_launch(m->dev, P, L, F, tk, denliq, denice, frq, aliq, aice, (cudaStream_t)stream);
@@ -437,6 +438,7 @@ int mwrt_plan_destroy(mwrt_plan* pl) {
   }
   if (pl->s_aux) cudaStreamDestroy(pl->s_aux);
   cudaFree(pl->d_frq); cudaFree(pl->d_angles); cudaFree(pl->d_amass); cudaFree(pl->d_bpw);
+  cudaFree(pl->abs_blocks.buf);
   delete pl;
   return 0;
 }
@@ -445,6 +447,15 @@ int mwrt_plan_set_emissivity(mwrt_plan* pl, double es) {
   if (!pl) return fail_arg(MWRT_E_ARG, "mwrt_plan_set_emissivity: null plan");
   pl->emis = es;
   return 0;
+}
+
+int mwrt_plan_absorption(mwrt_plan* pl, int P, const double* p, const double* tk, const double* e,
+                         double* awet, double* adry, int32_t* status, void* stream) {
+  if (!pl || !p || !tk || !e || !awet || !adry || P < 0)
+    return fail_arg(MWRT_E_ARG, "mwrt_plan_absorption: bad argument");
+  if (P == 0) return 0;
+  return absorption_launch(pl->model, P, pl->L, pl->F, p, tk, e, /*e_is_rh=*/0, nullptr, nullptr, pl->d_frq,
+                           awet, adry, status, pl->f32ls, &pl->abs_blocks, (cudaStream_t)stream);
 }
 
 int mwrt_plan_set_precision(mwrt_plan* pl, int precision) {
@@ -533,7 +544,7 @@ static int forward_chunk(mwrt_plan* pl, int slot, int P, const mwrt_profiles& in
   // kernel 1: vapour pressure + gas absorption (e is kept for the refractivity of kernel 2)
   nvtxRangePushA("mwrt:absorption");
   int rc = absorption_launch(pl->model, P, L, F, in.p, in.tk, in.rh, /*e_is_rh=*/1, w.e, nullptr, pl->d_frq,
-                             w.awet, w.adry, out.status, pl->f32ls, st_abs);
+                             w.awet, w.adry, out.status, pl->f32ls, &pl->abs_blocks, st_abs);
   nvtxRangePop();
   if (rc) return rc;
   // kernel 2: refractive slant path (the plane-parallel default needs no kernel: kernel 3 forms

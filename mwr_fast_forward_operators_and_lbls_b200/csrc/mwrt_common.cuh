@@ -41,6 +41,14 @@ struct ModelDev {
   const double* rows;    // device
   int n_rows;            // doubles in `rows`
 };
+// Per-plan cache of kernel 1's per-frequency-block scratch (k_abs_blocks in mwrt_absorption.cu): device
+// buffer + what it currently holds.
+struct AbsBlocks {
+  double* buf = nullptr;
+  size_t cap = 0;                          // doubles
+  int fb = 0, f32 = -1, far = -1, F = 0;
+  const double* frq = nullptr;
+};
 constexpr int kHS = MWRT_H2O_NCOL + 2;   // 20
 constexpr int kOS = MWRT_O2_NCOL + 2;    // 12
 constexpr int kH_IFL2 = MWRT_H2O_NCOL, kO_IFK2 = MWRT_O2_NCOL;

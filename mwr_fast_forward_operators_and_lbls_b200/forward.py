@@ -109,6 +109,20 @@ class Plan:
         arr = (C.c_int64 * max(len(offs), 1))(*offs)
         _lib.check(self.lib.mwrt_plan_set_output_fanout(self._h, code, len(offs), arr), "set_output_fanout")
 
+    def absorption(self, p, t, e, out=None):
+        """Kernel 1 alone on this plan's frequencies/model/precision (`mwrt_plan_absorption`): awet, adry
+        (P,F,L) CUDA tensors from p, t, e (P,L) CUDA tensors; the per-block tables are the plan's cached
+        ones (the plan-less `absorption()` rebuilds them per call)."""
+        P = p.shape[0]
+        for x, name in ((p, "p"), (t, "t"), (e, "e")):
+            self._check_dev(x, P, name)
+        if out is None:
+            out = (torch.empty((P, self.F, self.L), dtype=torch.float64, device="cuda"),
+                   torch.empty((P, self.F, self.L), dtype=torch.float64, device="cuda"))
+        _lib.check(self.lib.mwrt_plan_absorption(self._h, P, _ptr(p), _ptr(t), _ptr(e), _ptr(out[0]),
+                                                 _ptr(out[1]), None, _stream()), "plan_absorption")
+        return out
+
     def launch_count(self, P):
         return int(self.lib.mwrt_plan_launch_count(self._h, int(P)))
 

@@ -415,6 +415,38 @@ def test_absorption_block_width_switch(pkg, ora, nf, wide, monkeypatch):
     assert rel_err(cpu(g["adry"]), adry) < REL
 
 
+@pytest.mark.parametrize("model", ["R24", "R98", "R22SD"])
+@pytest.mark.parametrize("case", ["hatpro", "bands", "dense", "dense183", "wide_sweep", "sweep", "single",
+                                  "line_centres"])
+def test_far_lines_on_coarse_grid(pkg, ora, model, case, monkeypatch):
+    """Far lines are summed at the block's Chebyshev nodes and interpolated (kernel 1, kNQ): the result
+    must agree with the every-line-at-every-frequency form (MWRT_ABS_FAR=0) to 1e-10 and with the oracle
+    to the usual gate: sub-band sets and dense spectra (28/32-wide blocks, nearly everything far, incl.
+    blocks that hold line centres and the speed-dependent 183 GHz line), a wide sweep (nothing far), and
+    the narrow-block kernels, which do not carry the far-line code (HATPRO, a single frequency, line
+    centres)."""
+    d = pkg.synth_profiles(4, 37, seed=91)
+    e, _ = ora.pv.vapor(d["t"], d["rh"])
+    frq = {"hatpro": pkg.HATPRO_FRQ,
+           "bands": np.asarray(pkg.band_frequencies(50)).ravel()[:364],
+           "dense": np.arange(49.0, 51.24, 0.01),
+           "dense183": 182.0 + 0.01 * np.arange(224),
+           "wide_sweep": np.linspace(1.0, 1000.0, 224),
+           "sweep": np.linspace(1.0, 1000.0, 97),
+           "single": np.array([31.4]),
+           "line_centres": np.array([22.23508, 22.3, 60.306056, 60.4348, 118.750334, 118.8, 183.310087, 183.4,
+                                     325.152888, 380.197353, 424.763, 50.0, 90.0, 150.0])}[case]
+    monkeypatch.setenv("MWRT_ABS_FAR", "0")
+    full = pkg.absorption(model, d["p"], d["t"], e, frq)
+    monkeypatch.setenv("MWRT_ABS_FAR", "1")
+    far = pkg.absorption(model, d["p"], d["t"], e, frq)
+    for k in ("awet", "adry"):
+        assert rel_err(cpu(far[k]), cpu(full[k])) < 1e-10, k
+    awet, adry, _, _ = ora.pv.absorption(model, d["p"], d["t"], e, frq)
+    assert rel_err(cpu(far["awet"]), awet) < REL
+    assert rel_err(cpu(far["adry"]), adry) < REL
+
+
 def test_host_entry_large_pitch_fallback(pkg, monkeypatch):
     """A 2-D copy is only used while both pitches fit cudaDeviceProp::memPitch; beyond it the host entry
     moves one field per copy.  MWRT_MAX_PITCH fakes a tiny limit; results must not change."""
