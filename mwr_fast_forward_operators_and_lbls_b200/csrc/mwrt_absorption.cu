@@ -16,8 +16,11 @@
 //             for the FB frequencies, so the inner loop is ~11-13 DFMA-class ops + 1 MUFU.RCP64H per
 //             (line, frequency): both Lorentz wings share ONE reciprocal.
 //   tables  = the model's line tables are staged into shared memory once per CTA and read as
-//             warp-uniform broadcasts; (f -/+ f_line) is tabulated per CTA so the detuning keeps the
-//             oracle's rounding order.
+//             warp-uniform broadcasts; everything that depends on the frequency BLOCK only -- (f -/+ f_line)
+//             in the oracle's rounding order, line classes and processing orders, the far-line grid --
+//             is built once per plan by k_abs_blocks and copied by the CTAs.
+//   far     = wide blocks (28/32 frequencies): lines far from the block are summed at 6 Chebyshev nodes
+//             of the block and interpolated (see kNQ).
 // Absorption does not depend on the viewing angle: it is computed once and reused for all angles
 // (PyRTlib recomputes it per angle).
 #include "mwrt_common.cuh"
@@ -225,13 +228,14 @@ constexpr int kSlowNone = 0, kSlowCorr = 1, kSlowExact = 2;
 // smooth function of u = f^2 across the block: its poles sit at u = c3 +/- i sqrt(c4), a distance
 // |c3 - u0| >= rho * h away from the block [u0 - h, u0 + h].  The SUM of all such lines is evaluated
 // with the same pair loop at kNQ Chebyshev nodes of the block instead of at its FB frequencies and
-// interpolated once per level-point (Lagrange weights, tabulated per CTA): kNQ instead of FB
-// evaluations per far line.  Interpolation error <= ~2 (rho + sqrt(rho^2-1))^-kNQ of the far lines'
-// own contribution; kFarRho is chosen so that this is 1e-11 (two orders inside the 1e-9 parity gate;
-// measured against the oracle: <= 8e-12 of the line sum, tests/test_kernel_algebra.py).  The decision is
-// per CTA from the table centres with margins for the pressure shift (the 1 GHz the fast form allows)
-// and the width (w^2 <= 37 GHz^2).  HATPRO (14 channels, one block): 12 of 14 H2O and 11 of 49 O2 lines
-// are far; a 28- or 32-wide block of a dense spectrum sees nearly every line as far.
+// interpolated once per level-point (Lagrange weights, tabulated per block): kNQ instead of FB
+// evaluations per far line.  Interpolation error ~2 (rho + sqrt(rho^2-1))^-kNQ of the far lines' own
+// contribution; kFarRho is chosen so that this is ~1e-11 (measured against the full evaluation: <= 3e-11
+// of the line sum, tests/test_kernel_algebra.py; the parity gate on absorption is 1e-9).  The decision
+// is per frequency block (k_abs_blocks) from the table centres, with margins for the pressure shift (the
+// 1 GHz the fast form allows; the O2 mixing shift bound) and the width (w^2 <= 37 GHz^2).  A 28- or
+// 32-wide block of a sub-band set or dense spectrum sees nearly every line as far (config 3 K-band: 13 of
+// 14 H2O, 49 of 49 O2; 50-60 GHz blocks: 23-32 O2 lines); the 14 HATPRO channels as ONE block only 23 of 65.
 #ifndef MWRT_ABS_NQ
 #define MWRT_ABS_NQ 6
 #endif
@@ -334,9 +338,12 @@ __host__ __device__ inline int abs_block_doubles(int nh, int no, int FB, bool f3
 // Per-block scratch, ONE CTA per frequency block, once per (plan, knobs): the block's frequencies and
 // their squares, the Chebyshev nodes and Lagrange weights of the far-line grid, the exact detunings for
 // the slow paths, the line classes and processing orders, the fp32 detuning tables.  Kernel 1's CTAs
-// copy their block's record instead of rebuilding it (round 1 rebuilt it in each of 7 813 CTAs per
-// launch; the code of that prologue also swept the 32 KB instruction cache under the resident CTAs'
-// hot loops every time a CTA started -- measured: 5-12 % of kernel 1).
+// copy their block's record instead of rebuilding it.  Round 1 rebuilt it in each of 7 813 CTAs per
+// launch.  Measured on B200 (profiles/r02t_far_lines_experiments.txt): the per-CTA prologue cost 4 % of
+// kernel 1 in that form (config 2: 0.776 -> 0.748 ms with the copy) and 12-14 % once the far-line tables
+// were added to it, although it runs once per CTA -- more than its own instructions explain; the
+// likely mechanism is its code (~2 000 instructions) passing through the 32 KB instruction cache under
+// the resident CTAs' hot loops every time a CTA starts.
 template <int FB, bool F32>
 __global__ void __launch_bounds__(kAbsThreads)
 k_abs_blocks(const ModelDev m, const int F, const double* __restrict__ frq, const int far_on,
@@ -1218,9 +1225,11 @@ static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, c
     const bool hit = cache->buf && cache->fb == FB && cache->f32 == (int)F32 && cache->far == far_on &&
                      cache->F == F && cache->frq == frq;
     if (!hit) {
-      MWRT_CUDA_OK(cudaDeviceSynchronize());   // rare path: earlier launches on other streams may still read it
+      // a REbuild (knob or precision changed on a live plan): earlier launches on the plan's other
+      // streams may still read the old record
+      if (cache->buf) MWRT_CUDA_OK(cudaDeviceSynchronize());
       if (cache->cap < need) {
-        if (cache->buf) MWRT_CUDA_OK(cudaFree(cache->buf));   // (synchronises the device: nobody reads it any more)
+        if (cache->buf) MWRT_CUDA_OK(cudaFree(cache->buf));
         cache->buf = nullptr;
         cache->cap = 0;
         MWRT_CUDA_OK(cudaMalloc(&cache->buf, sizeof(double) * need));

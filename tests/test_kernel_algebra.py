@@ -305,3 +305,95 @@ def test_fp32_pair_form_keeps_the_cancellation_in_fp64():
     err = np.abs(got.astype(np.float64) - ref) / np.abs(ref)
     assert np.max(err[ok]) < 3e-5, np.max(err[ok])
     assert np.median(err) < 3e-7
+
+
+# ---- far lines on a coarse Chebyshev grid (kernel 1, kNQ = 6) -----------------------------------------
+_CHEB6 = np.cos((2 * np.arange(6) + 1) * np.pi / 12.0)
+_FAR_RHO = 34.1
+
+
+def _fast_forms(model, p, tk, e):
+    """(c3, c4, n1, n0) of every H2O and O2 line at the level-points (p, tk, e): the pair-loop form of
+    csrc/mwrt_absorption.cu (H2OLine / O2Line), in plain NumPy."""
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "..", "mwr_fast_forward_operators_and_lbls_b200",
+                                    "data", "models", model + ".json")))
+    h, o = d["h2o"], d["o2"]
+    rv = (0.01 * 8.314510) / 18.01528
+    rho = e / (rv * tk)
+    pvap = rho * tk / h["pvap_div"]
+    pda = p - pvap
+    ti = h["reftline"] / tk
+    tiln = np.log(ti)
+    hl = []
+    for i in range(len(h["fl"])):
+        w = h["w0"][i] * pda * ti ** h["x"][i] + h["w0s"][i] * pvap * ti ** h["xs"][i]
+        shift = (h["sr"][i] * w + h["sh"][i] * pda * (1 - h["aair"][i] * tiln) * ti ** h["xh"][i]
+                 + h["shs"][i] * pvap * (1 - h["aself"][i] * tiln) * ti ** h["xhs"][i])
+        sp = h["s1"][i] * ti ** 2.5 * np.exp(h["b2"][i] * (1 - ti)) / h["fl"][i] ** 2
+        fc2, wsq = (h["fl"][i] + shift) ** 2, w * w
+        hl.append((h["fl"][i], fc2 - wsq, 4 * fc2 * wsq, 2 * sp * w, 4 * sp * w * fc2))
+    th = 300.0 / tk
+    th1 = th - 1
+    preswv = rho * tk / o["pvap_div"]
+    den = 0.001 * ((p - preswv) * th ** o["x"] + o["h2o_broad"] * preswv * th)
+    pe2 = den * den
+    ol = []
+    for k in range(len(o["f"])):
+        df = o["w300"][k] * den
+        y = den * (o["y0"][k] + o["y1"][k] * th1)
+        g = 1 + pe2 * (o["g0"][k] + o["g1"][k] * th1)
+        fcen = o["f"][k] + pe2 * (o["dnu0"][k] + o["dnu1"][k] * th1)
+        sp = o["s300"][k] * np.exp(-o["be"][k] * th1) / o["f"][k] ** 2
+        a_s, pp, fc2, df2 = sp * df * g, sp * y * fcen, fcen ** 2, df * df
+        shmax = 4.0 * (abs(o["dnu0"][k]) + abs(o["dnu1"][k])) + 1e-6
+        ol.append((o["f"][k], fc2 - df2, 4 * fc2 * df2, 2 * (a_s + pp), 4 * (a_s * fc2 - pp * df2), shmax))
+    return hl, ol
+
+
+def test_far_lines_on_a_chebyshev_grid_match_the_full_sum():
+    """Kernel 1 sums the lines that are far from a frequency block (the per-block test of k_abs_blocks:
+    |f_line^2 - u0| - margins >= 34.1 half-widths of the block in u = f^2) at 6 Chebyshev nodes and
+    interpolates.  Against the full evaluation the line sum must not move by more than 1e-10 (measured:
+    3e-11; the parity gate on absorption is 1e-9) -- for the
+    HATPRO block, for 28-wide sub-band blocks and for 32-wide blocks of the dense spectrum."""
+    from mwr_fast_forward_operators_and_lbls_b200 import synth
+    from oracle import pyrtlib_vec as pv
+    d = synth.synth_profiles(40, 100, seed=5)
+    p, tk = d["p"].ravel(), d["t"].ravel()
+    e = pv.vapor(d["t"], d["rh"])[0].ravel()
+    hl, ol = _fast_forms("R24", p, tk, e)
+    bands = np.asarray(synth.band_frequencies(50)).ravel()
+    dense = np.asarray(synth.dense_spectrum())
+    blocks = [np.asarray(synth.HATPRO_FRQ)] + [bands[b * 28:(b + 1) * 28] for b in (0, 6, 13, 20, 24)] + \
+             [dense[b * 32:(b + 1) * 32] for b in (0, 7, 50, 100, 110, 120)]
+    worst, nfar_total = 0.0, 0
+    for frq in blocks:
+        u = frq ** 2
+        u0 = 0.5 * (u.min() + u.max())
+        hh = max(0.5 * (u.max() - u.min()), 1e-3 * u0)
+        xn = u0 + hh * _CHEB6
+        tt = (u - u0) / hh
+        M = np.ones((len(u), 6))
+        for n in range(6):
+            for q in range(6):
+                if q != n:
+                    M[:, n] *= (tt - _CHEB6[q]) / (_CHEB6[n] - _CHEB6[q])
+        for lines, is_h2o in ((hl, True), (ol, False)):
+            tot, err = 0.0, 0.0
+            for ln in lines:
+                fl, c3, c4, n1, n0 = ln[:5]
+                if is_h2o and not (fl + frq.max() < 749.0):      # only all-in lines take the pair form
+                    continue
+                margin = 2.0 * fl * (1.0 if is_h2o else ln[5]) + 37.0
+                g = lambda x: (n1[:, None] * (x[None, :] - c3[:, None]) + n0[:, None]) / \
+                    ((x[None, :] - c3[:, None]) ** 2 + c4[:, None])
+                full = g(u)
+                tot = tot + full
+                if abs(fl * fl - u0) - margin >= _FAR_RHO * hh:
+                    nfar_total += 1
+                    err = err + (g(xn) @ M.T - full)
+            worst = max(worst, float(np.max(np.abs(err) / np.abs(tot))))
+    assert nfar_total > 300          # the criterion is not vacuous: most lines of the narrow blocks are far
+    assert worst < 1e-10, worst
