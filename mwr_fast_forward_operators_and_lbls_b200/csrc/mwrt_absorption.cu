@@ -370,7 +370,6 @@ k_abs_blocks(const ModelDev m, const int F, const double* __restrict__ frq, cons
   constexpr int FBP = (FB + 3) & ~3;
   float* a32h = reinterpret_cast<float*>(smem + abs_smem_doubles(nh, no, FB));
   float* a32o = a32h + nh * FBP;
-  (void)a32h; (void)a32o; (void)unode; (void)mint; (void)oord;
   for (int i = threadIdx.x; i < m.n_rows; i += blockDim.x) hrow[i] = m.rows[i];
   for (int i = threadIdx.x; i < blk_stride; i += blockDim.x) fblk[i] = 0.0;   // padding is defined
   const int fb = blockIdx.x, f0 = fb * FB;
@@ -1244,12 +1243,18 @@ static int launch_abs(const ModelDev& m, int P, int L, int F, const double* p, c
   } else {
     MWRT_CUDA_OK(abs_scratch_alloc(&blocks, sizeof(double) * need, st));
     k_abs_blocks<FB, F32><<<nfb, kAbsThreads, smem, st>>>(m, F, frq, far_on, blocks, stride);
-    MWRT_CUDA_OK(cudaGetLastError());
   }
-  k_absorption<FB, F32><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, nfb, p, tk, e, e_is_rh, e_out,
-                                                         rho_out, frq, awet, adry, status, blocks, stride);
-  MWRT_CUDA_OK(cudaGetLastError());
-  if (!cache) MWRT_CUDA_OK(cudaFreeAsync(blocks, st));
+  cudaError_t err = cudaGetLastError();
+  if (err == cudaSuccess) {
+    k_absorption<FB, F32><<<grid, kAbsThreads, smem, st>>>(m, npts, L, F, nfb, p, tk, e, e_is_rh, e_out,
+                                                           rho_out, frq, awet, adry, status, blocks, stride);
+    err = cudaGetLastError();
+  }
+  if (!cache) {   // the per-call record goes back to the pool in stream order, launch error or not
+    const cudaError_t ferr = cudaFreeAsync(blocks, st);
+    if (err == cudaSuccess) err = ferr;
+  }
+  MWRT_CUDA_OK(err);
   return 0;
 }
 

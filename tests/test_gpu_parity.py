@@ -447,6 +447,26 @@ def test_far_lines_on_coarse_grid(pkg, ora, model, case, monkeypatch):
     assert rel_err(cpu(far["adry"]), adry) < REL
 
 
+def test_plan_absorption_equals_stage_entry(pkg, ora):
+    """mwrt_plan_absorption (kernel 1 on a plan, per-frequency-block tables cached in the plan) makes the
+    same launch as the plan-less mwrt_absorption_f64 / _f32ls: bitwise equal, narrow and wide blocks,
+    first call (record built) and second call (record reused)."""
+    import torch
+    L = 33
+    d = pkg.synth_profiles(5, L, seed=3)
+    e, _ = ora.pv.vapor(d["t"], d["rh"])
+    p_d, t_d, e_d = (torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).cuda()
+                     for x in (d["p"], d["t"], e))
+    for frq in (pkg.HATPRO_FRQ, 49.0 + 0.01 * np.arange(224)):
+        for f32 in (False, True):
+            plan = pkg.Plan("R24", L, frq, pkg.HATPRO_ELEV[:2], f32_lineshape=f32)
+            ref = pkg.absorption("R24", d["p"], d["t"], e, frq, f32_lineshape=f32)
+            for _ in range(2):
+                awet, adry = plan.absorption(p_d, t_d, e_d)
+                torch.cuda.synchronize()
+                assert torch.equal(awet, ref["awet"]) and torch.equal(adry, ref["adry"])
+
+
 def test_host_entry_large_pitch_fallback(pkg, monkeypatch):
     """A 2-D copy is only used while both pitches fit cudaDeviceProp::memPitch; beyond it the host entry
     moves one field per copy.  MWRT_MAX_PITCH fakes a tiny limit; results must not change."""
