@@ -298,7 +298,7 @@ __host__ __device__ inline int abs_smem_doubles(int nh, int no, int FB) {
 // pipe; everything hoisted per (level-point, line), the corrections (speed dependence, narrow lines),
 // the continua and the accumulation across lines stay fp64.  To keep the one cancellation of the pair
 // form out of fp32, vv = f^2 - c3 is formed as (f^2 - fl^2) - (c3 - fl^2): the first difference is
-// tabulated per CTA in fp64 and rounded once, the second is a small per-line quantity.  Strengths are
+// tabulated per frequency block in fp64 and rounded once, the second is a small per-line quantity.  Strengths are
 // scaled by 2^40 so that no term comes near the fp32 denormal range (undone exactly at the end).
 constexpr double kF32Scale = 1099511627776.0, kF32Unscale = 1.0 / 1099511627776.0;   // 2^40
 struct PairHotF {
@@ -420,7 +420,7 @@ k_abs_blocks(const ModelDev m, const int F, const double* __restrict__ frq, cons
       else if (fl - hi > 751.0 || lo - fl > 751.0) cls = kAllOut;
       // Corrections to the fast form are possible only for speed-dependent lines and for lines within
       // 1e-3*fl (+ the 1 GHz shift margin of the fast path) of a block frequency: decided here once
-      // per CTA, so the per-thread tests run for those lines only (HATPRO: the 22 GHz line).
+      // per block, so the per-thread tests run for those lines only (HATPRO: the 22 GHz line).
       const bool sd_cap = (m.h2o_sd != 0) && (hrow[i * kHS + MWRT_H2O_W2] != 0.0 || hrow[i * kHS + MWRT_H2O_W2S] != 0.0);
       const int chk = (sd_cap || dmin < 1e-3 * fl + 1.0) ? 1 : 0;
       hchk[i] = chk;
@@ -1081,7 +1081,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
           pair_accumulate<FB>(acc, fsq2, h);
         }
         cur = nxt;
-        if (!(ochk[ka] | ochk[kb])) continue;   // uniform, decided per CTA
+        if (!(ochk[ka] | ochk[kb])) continue;   // uniform, decided per block
         o2_corrections(ka, kb);
       }   // pairs
       }
@@ -1116,7 +1116,7 @@ k_absorption(const ModelDev m, const long long npts, const int L, const int F, c
         const PairHot h{oa.c3, oa.c4, oa.n1, oa.n0, ob.c3, ob.c4, ob.n1, ob.n0};
         pair_accumulate<FB>(acc, fsq2, h);
         }
-        if (!(ochk[ka] | ochk[kb])) continue;   // uniform, decided per CTA
+        if (!(ochk[ka] | ochk[kb])) continue;   // uniform, decided per block
         o2_corrections(ka, kb);
       }   // pairs of the group
     }     // groups
